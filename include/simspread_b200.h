@@ -1,0 +1,178 @@
+/*
+ * simspread_b200.h -- C ABI of libsimspread_b200.so
+ *
+ * B200 (sm_100a) implementation of the resource-spreading hot path of SimSpread.jl:
+ *   featurize/cutoff -> construct (+ degrees k) -> spread -> predict -> clean! -> ranking metrics.
+ *
+ * The reference (cvigilv/SimSpread.jl) is pure Julia and has no FFI of its own; the boundary this
+ * header replaces is the set of exported Julia generics (src/SimSpread.jl:21-56).  Every entry
+ * point below names the reference function (file:line, relative to the reference checkout) whose
+ * array work it performs.  The Julia wrappers (`simspread.jl_b200/julia/`) and the Python ctypes
+ * mirror (`simspread.jl_b200/host.py`) bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int32 status (SS_OK == 0); the message of the last failure on the
+ *     calling thread is available from ss_last_error().  No C++ exception crosses the ABI.
+ *   - host buffers are caller-owned, COLUMN-MAJOR float64 with an explicit leading dimension
+ *     (Julia `Matrix{Float64}` layout), valid for the duration of the call only.
+ *   - device memory is library-owned behind opaque handles (ss_mat, ss_ivec, ss_csr) unless it was
+ *     wrapped with ss_mat_wrap()/ss_ivec_wrap(); handles are destroyed explicitly.
+ *   - indices inside the ABI are 0-based int32 (the Julia wrapper converts from 1-based).
+ *   - one ss_ctx per GPU; calls on a context are issued on its stream and are synchronous on
+ *     return unless the name ends in _async.  There is NO CPU fallback: without a CUDA device
+ *     ss_ctx_create() fails with SS_ERR_NO_DEVICE.
+ */
+#ifndef SIMSPREAD_B200_H
+#define SIMSPREAD_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SS_API __attribute__((visibility("default")))
+#else
+#define SS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define SS_OK 0
+#define SS_ERR_INVALID 1     /* bad argument (shape, null pointer, alignment) */
+#define SS_ERR_CUDA 2        /* a CUDA runtime/driver call failed */
+#define SS_ERR_NO_DEVICE 3   /* no usable sm_100 device: there is no CPU fallback */
+#define SS_ERR_ASSERT 4      /* a reference @assert fired; ss_last_error() holds its message */
+#define SS_ERR_OOM 5         /* device or pinned-host allocation failed */
+#define SS_ERR_UNSUPPORTED 6 /* valid request that this build does not implement */
+
+/* ss_predict_* flags */
+#define SS_PREDICT_CLEAN 1u /* fuse clean! (src/core.jl:478-484): columns with kt == 0 -> -99 */
+
+/* ss_gemm_f64 operand form of A */
+#define SS_OP_N 0 /* A is M x K column-major (m contiguous)            : C = A  * B */
+#define SS_OP_T 1 /* A is stored K x M column-major (k contiguous)     : C = A' * B */
+
+typedef struct ss_ctx ss_ctx;   /* one GPU + one stream + workspaces */
+typedef struct ss_mat ss_mat;   /* dense float64 column-major device matrix */
+typedef struct ss_ivec ss_ivec; /* int32 device vector (degrees, index lists) */
+typedef struct ss_csr ss_csr;   /* CSR device matrix (int32 row_ptr/col_idx, optional f64 values) */
+
+/* ---- library / context ------------------------------------------------------------------- */
+SS_API int32_t ss_version(void);
+SS_API const char* ss_last_error(void);
+SS_API int32_t ss_device_count(int32_t* count);
+SS_API int32_t ss_ctx_create(int32_t device, ss_ctx** out);
+SS_API int32_t ss_ctx_destroy(ss_ctx* ctx);
+SS_API int32_t ss_ctx_sync(ss_ctx* ctx);
+/* the CUDA stream the context launches on (a cudaStream_t), for event timing by the caller */
+SS_API int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out);
+/* number of kernels launched on this context since creation (bench.py's gpu_launches) */
+SS_API int32_t ss_ctx_launch_count(ss_ctx* ctx, int64_t* count);
+/* Per-kernel device timing of the chain-product GEMMs (CUDA events on the context stream, recorded
+ * around each launch while enabled).  ss_ctx_profile_read() synchronises, returns up to `cap`
+ * (milliseconds, algorithmic flops = 2*M*N*K) pairs in launch order and clears the list. */
+SS_API int32_t ss_ctx_profile(ss_ctx* ctx, int32_t enable);
+SS_API int32_t ss_ctx_profile_read(ss_ctx* ctx, double* ms_out, double* flops_out, int32_t cap, int32_t* n_out);
+SS_API int32_t ss_host_alloc(int64_t bytes, void** out); /* pinned host memory */
+SS_API int32_t ss_host_free(void* p);
+
+/* ---- device containers ------------------------------------------------------------------- */
+/* zero-initialised rows x cols matrix; ld is padded to a multiple of 16 elements (TMA alignment) */
+SS_API int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out);
+/* non-owning view of caller-managed device memory (16-byte aligned, ld even, ld >= rows) */
+SS_API int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols, int64_t ld, ss_mat** out);
+SS_API int32_t ss_mat_destroy(ss_mat* m);
+SS_API int32_t ss_mat_info(const ss_mat* m, int64_t* rows, int64_t* cols, int64_t* ld, void** devptr);
+SS_API int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host);
+SS_API int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_host);
+/* column range [col0, col0+ncols) only; asynchronous on the context stream (pinned host memory) */
+SS_API int32_t ss_mat_upload_cols_async(ss_ctx* ctx, ss_mat* m, int64_t col0, int64_t ncols,
+                                 const double* host, int64_t ld_host);
+SS_API int32_t ss_mat_download_cols_async(ss_ctx* ctx, const ss_mat* m, int64_t col0, int64_t ncols,
+                                   double* host, int64_t ld_host);
+SS_API int32_t ss_ivec_create(ss_ctx* ctx, int64_t n, ss_ivec** out);
+SS_API int32_t ss_ivec_wrap(ss_ctx* ctx, void* devptr, int64_t n, ss_ivec** out);
+SS_API int32_t ss_ivec_destroy(ss_ivec* v);
+SS_API int32_t ss_ivec_info(const ss_ivec* v, int64_t* n, void** devptr);
+SS_API int32_t ss_ivec_upload(ss_ctx* ctx, ss_ivec* v, const int32_t* host);
+SS_API int32_t ss_ivec_download(ss_ctx* ctx, const ss_ivec* v, int32_t* host);
+
+/* ---- (1) featurization ------------------------------------------------------------------- */
+/* cutoff.(S, alpha, weighted)  [src/core.jl:37-43 scalar rule, :55-60 array, :106-112 featurize,
+ * :129-132 featurize!]: X[i,j] = S[i,j] >= alpha ? (weighted ? S[i,j] : 1.0) : 0.0 (NaN -> 0).
+ * X may be S itself (featurize!).  One pass, 128-bit loads/stores. */
+SS_API int32_t ss_featurize(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_mat* X);
+/* Same threshold, output compacted to CSR of S (row = source, ascending column index) by a
+ * warp-ballot kernel; values are stored when weighted != 0.  An entry is kept iff the
+ * thresholded value is an edge for src/graphs.jl:10 (non-zero). */
+SS_API int32_t ss_featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out);
+SS_API int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values);
+SS_API int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t* col_idx, double* values);
+SS_API int32_t ss_csr_destroy(ss_csr* c);
+
+/* ---- (2) graph construction + degrees ------------------------------------------------------ */
+/* Block extraction of construct() [src/core.jl:167,171-172: X[queries,features], X[sources,features],
+ * y[sources,targets]]: dst[i,j] = src[row_idx[i], col_idx[j]]; a NULL index list means identity. */
+SS_API int32_t ss_gather(ss_ctx* ctx, const ss_mat* src, const ss_ivec* row_idx, const ss_ivec* col_idx, ss_mat* dst);
+/* Degrees of the masked graph B [src/graphs.jl:9-11 applied to the B of src/core.jl:196-198]:
+ * ks[s] = nnz(Xs[s,:]) + nnz(Y[s,:]), kf[f] = nnz(Xs[:,f]), kt[t] = nnz(Y[:,t]).
+ * Non-zero test is !iszero (NaN counts, -0.0 does not).  Xs may be NULL (2-layer NBI); any output
+ * may be NULL. */
+SS_API int32_t ss_degrees(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_ivec* ks, ss_ivec* kf, ss_ivec* kt);
+/* k(G) = mapslices(k, G; dims=2) [src/graphs.jl:11]: row non-zero counts of any dense matrix. */
+SS_API int32_t ss_k_rows(ss_ctx* ctx, const ss_mat* G, ss_ivec* k);
+
+/* ---- (3) spread + predict ------------------------------------------------------------------ */
+/* spread [src/core.jl:365-371]: W[i,j] = G[i,j] / k[i] (true division), Inf -> 0, NaN -> 0.
+ * k == NULL computes k(G) first (the literal reference call); W may alias G. */
+SS_API int32_t ss_spread_rows(ss_ctx* ctx, const ss_mat* G, const ss_ivec* k, ss_mat* W);
+/* One step of the chain product: C = op(A) * B on the FP64 tensor pipe (TMA-staged, DMMA), with the
+ * degree normalisation fused in the epilogue:
+ *   row_div  != NULL : C[m,n] = acc / row_div[m]   (0 when row_div[m] == 0)   -- the 1/kf of W[f,:]
+ *   col_flag != NULL : C[m,n] = -99 where col_flag[n] == 0                     -- clean!
+ * B is K x N column-major. */
+SS_API int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
+                    const ss_ivec* row_div, const ss_ivec* col_flag);
+/* predict((A,B), ytest) for query rows [src/core.jl:402-423 with the blocks of :165-198]:
+ *   R = Xq * T,  T = (Xs' ./ kf) * (Y ./ ks)      
+ * Xq: Nq x Nf, Xs: Ns x Nf, Y: Ns x Nt, R: Nq x Nt.  Runs degrees -> spread -> T -> R on the
+ * context stream.  kt_out (optional) receives the target degrees used by clean!. */
+SS_API int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
+                         uint32_t flags, ss_ivec* kt_out);
+/* predict(A, ytrain) / source rows [src/core.jl:446-466]: R = Xs*T + Y*U, U = (Y' ./ kt)*(Y ./ ks).
+ * Xs may be NULL (classical 2-layer NBI: R = Y*U). */
+SS_API int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags);
+/* clean! [src/core.jl:478-484]: R[:,t] = -99 for every t with kt[t] == 0. */
+SS_API int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt);
+
+/* Reference-facing one-call form with HOST buffers (what the Julia `predict` wrapper ccalls):
+ * uploads Xq/Xs/Y, runs ss_predict_query, downloads R.  Xq slabs / R slabs are pipelined against
+ * the R GEMM on separate streams when the host buffers are pinned. */
+SS_API int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const double* Xs, int64_t ldxs,
+                              const double* Y, int64_t ldy, int64_t nq, int64_t ns, int64_t nf, int64_t nt,
+                              uint32_t flags, double* R, int64_t ldr);
+
+/* ---- (4) ranking + metrics ----------------------------------------------------------------- */
+/* Per-row top-L of R under `sortperm(row; rev=true)` order [src/performance.jl:315,377]:
+ * descending by isless, ties by ascending column.  idx_out: L x rows int32 (column-major, 0-based
+ * columns), val_out (optional): L x rows. */
+SS_API int32_t ss_topl_rows(ss_ctx* ctx, const ss_mat* R, int32_t L, ss_ivec* idx_out, ss_mat* val_out);
+/* mean recall@L / precision@L over the rows (groups) of R [src/performance.jl:341-357, 398-414]:
+ * out[0] = mean recall@L (NaN if any row of Ytrue has no positive, as in the reference),
+ * out[1] = mean precision@L.  Requires cols > L (the reference's strict assert, :311-312). */
+SS_API int32_t ss_atl(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t L, double* out2);
+/* AuROC / AuPRC over M (label, score) pairs [src/performance.jl:49-63, 74-89; MLBase.roc,
+ * Trapz.trapz semantics]: device radix sort + scan.  labels: uint8 (non-zero = positive),
+ * scores: float64, both device pointers.  out[0] = AuROC, out[1] = AuPRC. */
+SS_API int32_t ss_auroc_auprc(ss_ctx* ctx, const void* labels_u8_dev, const void* scores_f64_dev, int64_t M,
+                       double* out2);
+/* Same for the entries of two device matrices (Ytrue != 0 is the label), column-major order. */
+SS_API int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, double* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMSPREAD_B200_H */

@@ -1,0 +1,700 @@
+// C ABI of libsimspread_b200.so (see include/simspread_b200.h): contexts, device containers, and
+// the orchestration of the predict chain.  Kernels live in ss_elementwise.cu / ss_gemm.cu /
+// ss_rank.cu / ss_csr.cu.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ss_common.cuh"
+
+namespace ss {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int32_t scratch_get(ss_ctx* ctx, int slot, size_t bytes, void** out) {
+    Scratch& s = ctx->ws[slot];
+    if (s.bytes < bytes) {
+        if (s.p) {
+            SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+            SS_CHECK_CUDA(cudaFree(s.p));
+            s.p = nullptr;
+            s.bytes = 0;
+        }
+        size_t want = (bytes + 255) & ~size_t(255);
+        SS_CHECK_CUDA(cudaMalloc(&s.p, want));
+        s.bytes = want;
+    }
+    *out = s.p;
+    return SS_OK;
+}
+
+}  // namespace ss
+
+using namespace ss;
+
+#define SS_ENTER(ctx)                                                   \
+    SS_REQUIRE((ctx) != nullptr, "%s: null context", __func__);         \
+    SS_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+int32_t ss_version(void) { return SS_VERSION; }
+const char* ss_last_error(void) { return g_err; }
+
+int32_t ss_device_count(int32_t* count) {
+    SS_REQUIRE(count, "ss_device_count: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return SS_OK;
+}
+
+int32_t ss_ctx_create(int32_t device, ss_ctx** out) {
+    SS_REQUIRE(out, "ss_ctx_create: null output");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device is visible: libsimspread_b200 has no CPU fallback");
+        return SS_ERR_NO_DEVICE;
+    }
+    SS_REQUIRE(device >= 0 && device < n, "ss_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    SS_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return SS_ERR_NO_DEVICE;
+    }
+    SS_CHECK_CUDA(cudaSetDevice(device));
+    ss_ctx* c = new ss_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    *out = c;
+    return SS_OK;
+}
+
+int32_t ss_ctx_destroy(ss_ctx* ctx) {
+    if (!ctx) return SS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->ws)
+        if (s.p) cudaFree(s.p);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+    return SS_OK;
+}
+
+int32_t ss_ctx_sync(ss_ctx* ctx) {
+    SS_ENTER(ctx);
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_in));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_out));
+    return SS_OK;
+}
+
+int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out) {
+    SS_REQUIRE(ctx && stream_out, "ss_ctx_stream: null argument");
+    *stream_out = reinterpret_cast<void*>(ctx->stream);
+    return SS_OK;
+}
+
+int32_t ss_ctx_launch_count(ss_ctx* ctx, int64_t* count) {
+    SS_REQUIRE(ctx && count, "ss_ctx_launch_count: null argument");
+    *count = ctx->launches;
+    return SS_OK;
+}
+
+int32_t ss_ctx_profile(ss_ctx* ctx, int32_t enable) {
+    SS_ENTER(ctx);
+    ctx->profile = enable != 0;
+    return SS_OK;
+}
+
+int32_t ss_ctx_profile_read(ss_ctx* ctx, double* ms_out, double* flops_out, int32_t cap, int32_t* n_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(n_out && cap >= 0, "ss_ctx_profile_read: bad argument");
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    int32_t n = 0;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (n < cap) {
+            if (ms_out) ms_out[n] = ms;
+            if (flops_out) flops_out[n] = r.flops;
+            ++n;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    ctx->prof.clear();
+    *n_out = n;
+    return SS_OK;
+}
+
+int32_t ss_host_alloc(int64_t bytes, void** out) {
+    SS_REQUIRE(out && bytes >= 0, "ss_host_alloc: bad argument");
+    *out = nullptr;
+    if (bytes == 0) return SS_OK;
+    SS_CHECK_CUDA(cudaHostAlloc(out, size_t(bytes), cudaHostAllocDefault));
+    return SS_OK;
+}
+
+int32_t ss_host_free(void* p) {
+    if (p) SS_CHECK_CUDA(cudaFreeHost(p));
+    return SS_OK;
+}
+
+// ---- containers ------------------------------------------------------------------------------
+
+int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out && rows >= 0 && cols >= 0, "ss_mat_create: bad shape %lld x %lld", (long long)rows,
+               (long long)cols);
+    ss_mat* m = new ss_mat();
+    m->ctx = ctx;
+    m->rows = rows;
+    m->cols = cols;
+    m->ld = round_up(rows > 0 ? rows : 1, 16);
+    m->owned = true;
+    const size_t bytes = size_t(m->ld) * size_t(cols > 0 ? cols : 1) * 8 + 256;
+    cudaError_t e = cudaMalloc(&m->d, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete m;
+        set_error("ss_mat_create: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return SS_ERR_OOM;
+    }
+    SS_CHECK_CUDA(cudaMemsetAsync(m->d, 0, bytes, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return SS_OK;
+}
+
+int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols, int64_t ld, ss_mat** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out && devptr && rows >= 0 && cols >= 0, "ss_mat_wrap: bad argument");
+    SS_REQUIRE(ld >= rows && (ld % 2) == 0, "ss_mat_wrap: ld (%lld) must be even and >= rows (%lld)",
+               (long long)ld, (long long)rows);
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(devptr) & 15) == 0, "ss_mat_wrap: pointer must be 16-byte aligned");
+    ss_mat* m = new ss_mat();
+    m->ctx = ctx;
+    m->d = static_cast<double*>(devptr);
+    m->rows = rows;
+    m->cols = cols;
+    m->ld = ld;
+    m->owned = false;
+    *out = m;
+    return SS_OK;
+}
+
+int32_t ss_mat_destroy(ss_mat* m) {
+    if (!m) return SS_OK;
+    if (m->owned && m->d) {
+        cudaSetDevice(m->ctx->device);
+        cudaFree(m->d);
+    }
+    delete m;
+    return SS_OK;
+}
+
+int32_t ss_mat_info(const ss_mat* m, int64_t* rows, int64_t* cols, int64_t* ld, void** devptr) {
+    SS_REQUIRE(m, "ss_mat_info: null matrix");
+    if (rows) *rows = m->rows;
+    if (cols) *cols = m->cols;
+    if (ld) *ld = m->ld;
+    if (devptr) *devptr = m->d;
+    return SS_OK;
+}
+
+static int32_t copy2d(ss_ctx* ctx, cudaStream_t st, void* dst, int64_t dpitch, const void* src, int64_t spitch,
+                      int64_t rows, int64_t cols, cudaMemcpyKind kind) {
+    if (rows == 0 || cols == 0) return SS_OK;
+    SS_CHECK_CUDA(cudaMemcpy2DAsync(dst, size_t(dpitch) * 8, src, size_t(spitch) * 8, size_t(rows) * 8,
+                                    size_t(cols), kind, st));
+    return SS_OK;
+}
+
+int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_upload: null argument");
+    SS_REQUIRE(ld_host >= m->rows, "ss_mat_upload: ld_host (%lld) < rows (%lld)", (long long)ld_host,
+               (long long)m->rows);
+    SS_TRY(copy2d(ctx, ctx->stream, m->d, m->ld, host, ld_host, m->rows, m->cols, cudaMemcpyHostToDevice));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_download: null argument");
+    SS_REQUIRE(ld_host >= m->rows, "ss_mat_download: ld_host (%lld) < rows (%lld)", (long long)ld_host,
+               (long long)m->rows);
+    SS_TRY(copy2d(ctx, ctx->stream, host, ld_host, m->d, m->ld, m->rows, m->cols, cudaMemcpyDeviceToHost));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_mat_upload_cols_async(ss_ctx* ctx, ss_mat* m, int64_t col0, int64_t ncols, const double* host,
+                                 int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && host && col0 >= 0 && ncols >= 0 && col0 + ncols <= m->cols && ld_host >= m->rows,
+               "ss_mat_upload_cols_async: bad argument");
+    return copy2d(ctx, ctx->stream, m->d + col0 * m->ld, m->ld, host, ld_host, m->rows, ncols,
+                  cudaMemcpyHostToDevice);
+}
+
+int32_t ss_mat_download_cols_async(ss_ctx* ctx, const ss_mat* m, int64_t col0, int64_t ncols, double* host,
+                                   int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && host && col0 >= 0 && ncols >= 0 && col0 + ncols <= m->cols && ld_host >= m->rows,
+               "ss_mat_download_cols_async: bad argument");
+    return copy2d(ctx, ctx->stream, host, ld_host, m->d + col0 * m->ld, m->ld, m->rows, ncols,
+                  cudaMemcpyDeviceToHost);
+}
+
+int32_t ss_ivec_create(ss_ctx* ctx, int64_t n, ss_ivec** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out && n >= 0, "ss_ivec_create: bad argument");
+    ss_ivec* v = new ss_ivec();
+    v->ctx = ctx;
+    v->n = n;
+    v->owned = true;
+    const size_t bytes = size_t(n > 0 ? n : 1) * 4 + 64;
+    cudaError_t e = cudaMalloc(&v->d, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete v;
+        set_error("ss_ivec_create: cudaMalloc of %zu bytes failed", bytes);
+        return SS_ERR_OOM;
+    }
+    SS_CHECK_CUDA(cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = v;
+    return SS_OK;
+}
+
+int32_t ss_ivec_wrap(ss_ctx* ctx, void* devptr, int64_t n, ss_ivec** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out && devptr && n >= 0, "ss_ivec_wrap: bad argument");
+    ss_ivec* v = new ss_ivec();
+    v->ctx = ctx;
+    v->d = static_cast<int32_t*>(devptr);
+    v->n = n;
+    v->owned = false;
+    *out = v;
+    return SS_OK;
+}
+
+int32_t ss_ivec_destroy(ss_ivec* v) {
+    if (!v) return SS_OK;
+    if (v->owned && v->d) {
+        cudaSetDevice(v->ctx->device);
+        cudaFree(v->d);
+    }
+    delete v;
+    return SS_OK;
+}
+
+int32_t ss_ivec_info(const ss_ivec* v, int64_t* n, void** devptr) {
+    SS_REQUIRE(v, "ss_ivec_info: null vector");
+    if (n) *n = v->n;
+    if (devptr) *devptr = v->d;
+    return SS_OK;
+}
+
+int32_t ss_ivec_upload(ss_ctx* ctx, ss_ivec* v, const int32_t* host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(v && (host || v->n == 0), "ss_ivec_upload: null argument");
+    if (v->n) SS_CHECK_CUDA(cudaMemcpyAsync(v->d, host, size_t(v->n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_ivec_download(ss_ctx* ctx, const ss_ivec* v, int32_t* host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(v && (host || v->n == 0), "ss_ivec_download: null argument");
+    if (v->n) SS_CHECK_CUDA(cudaMemcpyAsync(host, v->d, size_t(v->n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// ---- (1) featurize -----------------------------------------------------------------------------
+
+int32_t ss_featurize(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_mat* X) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(S && X, "ss_featurize: null matrix");
+    SS_REQUIRE(S->rows == X->rows && S->cols == X->cols, "ss_featurize: shape mismatch");
+    SS_TRY(launch_featurize(ctx, S->d, S->rows, S->cols, S->ld, alpha, weighted != 0, X->d, X->ld));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(S && out, "ss_featurize_csr: null argument");
+    SS_TRY(featurize_csr(ctx, S, alpha, weighted != 0, out));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values) {
+    SS_REQUIRE(c, "ss_csr_info: null csr");
+    if (rows) *rows = c->rows;
+    if (cols) *cols = c->cols;
+    if (nnz) *nnz = c->nnz;
+    if (has_values) *has_values = c->values ? 1 : 0;
+    return SS_OK;
+}
+
+int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t* col_idx, double* values) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(c, "ss_csr_download: null csr");
+    if (row_ptr)
+        SS_CHECK_CUDA(cudaMemcpyAsync(row_ptr, c->row_ptr, size_t(c->rows + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (col_idx && c->nnz)
+        SS_CHECK_CUDA(cudaMemcpyAsync(col_idx, c->col_idx, size_t(c->nnz) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (values && c->values && c->nnz)
+        SS_CHECK_CUDA(cudaMemcpyAsync(values, c->values, size_t(c->nnz) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_csr_destroy(ss_csr* c) {
+    if (!c) return SS_OK;
+    cudaSetDevice(c->ctx->device);
+    if (c->row_ptr) cudaFree(c->row_ptr);
+    if (c->col_idx) cudaFree(c->col_idx);
+    if (c->values) cudaFree(c->values);
+    delete c;
+    return SS_OK;
+}
+
+// ---- (2) construct / degrees -------------------------------------------------------------------
+
+int32_t ss_gather(ss_ctx* ctx, const ss_mat* src, const ss_ivec* row_idx, const ss_ivec* col_idx, ss_mat* dst) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(src && dst, "ss_gather: null matrix");
+    SS_REQUIRE((row_idx ? row_idx->n : src->rows) == dst->rows && (col_idx ? col_idx->n : src->cols) == dst->cols,
+               "ss_gather: destination shape does not match the index lists");
+    SS_TRY(launch_gather(ctx, src->d, src->ld, row_idx ? row_idx->d : nullptr, col_idx ? col_idx->d : nullptr,
+                         dst->d, dst->rows, dst->cols, dst->ld));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+static int32_t degrees_async(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, int32_t* ks, int32_t* kf, int32_t* kt) {
+    const int64_t ns = Y->rows;
+    if (ks) SS_CHECK_CUDA(cudaMemsetAsync(ks, 0, size_t(ns) * 4, ctx->stream));
+    if (kf && Xs) SS_CHECK_CUDA(cudaMemsetAsync(kf, 0, size_t(Xs->cols) * 4, ctx->stream));
+    if (kt) SS_CHECK_CUDA(cudaMemsetAsync(kt, 0, size_t(Y->cols) * 4, ctx->stream));
+    if (Xs && (ks || kf)) SS_TRY(launch_degrees(ctx, Xs->d, Xs->rows, Xs->cols, Xs->ld, ks, kf));
+    if (ks || kt) SS_TRY(launch_degrees(ctx, Y->d, Y->rows, Y->cols, Y->ld, ks, kt));
+    return SS_OK;
+}
+
+int32_t ss_degrees(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_ivec* ks, ss_ivec* kf, ss_ivec* kt) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Y, "ss_degrees: Y is required");
+    SS_REQUIRE(!Xs || Xs->rows == Y->rows, "ss_degrees: Xs and Y must have the same number of source rows");
+    SS_REQUIRE(!ks || ks->n == Y->rows, "ss_degrees: ks has wrong length");
+    SS_REQUIRE(!kf || (Xs && kf->n == Xs->cols), "ss_degrees: kf has wrong length");
+    SS_REQUIRE(!kt || kt->n == Y->cols, "ss_degrees: kt has wrong length");
+    SS_TRY(degrees_async(ctx, Xs, Y, ks ? ks->d : nullptr, kf ? kf->d : nullptr, kt ? kt->d : nullptr));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_k_rows(ss_ctx* ctx, const ss_mat* G, ss_ivec* k) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(G && k && k->n == G->rows, "ss_k_rows: bad argument");
+    if (k->n) SS_CHECK_CUDA(cudaMemsetAsync(k->d, 0, size_t(k->n) * 4, ctx->stream));
+    SS_TRY(launch_degrees(ctx, G->d, G->rows, G->cols, G->ld, k->d, nullptr));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// ---- (3) spread / predict ----------------------------------------------------------------------
+
+int32_t ss_spread_rows(ss_ctx* ctx, const ss_mat* G, const ss_ivec* k, ss_mat* W) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(G && W && G->rows == W->rows && G->cols == W->cols, "ss_spread_rows: shape mismatch");
+    const int32_t* kd = nullptr;
+    if (k) {
+        SS_REQUIRE(k->n == G->rows, "ss_spread_rows: k has wrong length");
+        kd = k->d;
+    } else {
+        void* p;
+        SS_TRY(scratch_get(ctx, 0, size_t(G->rows + 1) * 4, &p));
+        SS_CHECK_CUDA(cudaMemsetAsync(p, 0, size_t(G->rows + 1) * 4, ctx->stream));
+        SS_TRY(launch_degrees(ctx, G->d, G->rows, G->cols, G->ld, static_cast<int32_t*>(p), nullptr));
+        kd = static_cast<int32_t*>(p);
+    }
+    SS_TRY(launch_spread_rows(ctx, G->d, G->rows, G->cols, G->ld, kd, W->d, W->ld));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C, const ss_ivec* row_div,
+                    const ss_ivec* col_flag) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(A && B && C, "ss_gemm_f64: null matrix");
+    SS_REQUIRE(opA == SS_OP_N || opA == SS_OP_T, "ss_gemm_f64: bad opA");
+    const int64_t M = (opA == SS_OP_N) ? A->rows : A->cols;
+    const int64_t K = (opA == SS_OP_N) ? A->cols : A->rows;
+    SS_REQUIRE(B->rows == K && C->rows == M && C->cols == B->cols, "ss_gemm_f64: shape mismatch");
+    SS_REQUIRE(!row_div || row_div->n == M, "ss_gemm_f64: row_div has wrong length");
+    SS_REQUIRE(!col_flag || col_flag->n == B->cols, "ss_gemm_f64: col_flag has wrong length");
+    SS_TRY(launch_gemm_f64(ctx, opA, A->d, A->ld, B->d, B->ld, C->d, C->ld, M, B->cols, K,
+                           row_div ? row_div->d : nullptr, col_flag ? col_flag->d : nullptr, false));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// Shared front half of both predict forms: degrees -> Wst = Y ./ ks -> T = (Xs' * Wst) ./ kf.
+// Returns device pointers into the context workspaces.
+struct ChainWs {
+    int32_t *ks = nullptr, *kf = nullptr, *kt = nullptr;
+    double* Wst = nullptr;
+    int64_t ldw = 0;
+    double* T = nullptr;
+    int64_t ldt = 0;
+};
+
+static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ChainWs* w) {
+    const int64_t ns = Y->rows, nt = Y->cols, nf = Xs ? Xs->cols : 0;
+    void* p;
+    const size_t kbytes = size_t(round_up(ns, 64) + round_up(nf, 64) + round_up(nt, 64)) * 4;
+    SS_TRY(scratch_get(ctx, 0, kbytes, &p));
+    w->ks = static_cast<int32_t*>(p);
+    w->kf = w->ks + round_up(ns, 64);
+    w->kt = w->kf + round_up(nf, 64);
+    SS_TRY(degrees_async(ctx, Xs, Y, w->ks, Xs ? w->kf : nullptr, w->kt));
+    w->ldw = round_up(ns, 16);
+    SS_TRY(scratch_get(ctx, 1, size_t(w->ldw) * size_t(nt) * 8, &p));
+    w->Wst = static_cast<double*>(p);
+    SS_TRY(launch_spread_rows(ctx, Y->d, ns, nt, Y->ld, w->ks, w->Wst, w->ldw));
+    if (Xs) {
+        w->ldt = round_up(nf, 16);
+        SS_TRY(scratch_get(ctx, 2, size_t(w->ldt) * size_t(nt) * 8, &p));
+        w->T = static_cast<double*>(p);
+        // T[f,t] = (sum_s Xs[s,f] * Wst[s,t]) / kf[f]
+        SS_TRY(launch_gemm_f64(ctx, SS_OP_T, Xs->d, Xs->ld, w->Wst, w->ldw, w->T, w->ldt, nf, nt, ns, w->kf,
+                               nullptr, false));
+    }
+    return SS_OK;
+}
+
+int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags,
+                         ss_ivec* kt_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Xq && Xs && Y && R, "ss_predict_query: null matrix");
+    SS_REQUIRE(Xq->cols == Xs->cols, "Number of features between test and training sets doesn't match");
+    SS_REQUIRE(Xs->rows == Y->rows, "Labels and features have different number of source nodes");
+    SS_REQUIRE(R->rows == Xq->rows && R->cols == Y->cols, "ss_predict_query: R must be Nq x Nt");
+    SS_REQUIRE(!kt_out || kt_out->n == Y->cols, "ss_predict_query: kt_out has wrong length");
+    if (R->rows == 0 || R->cols == 0) return SS_OK;
+    if (Xs->rows == 0 || Xs->cols == 0) {  // no sources / no features: every product is empty -> zeros
+        SS_CHECK_CUDA(cudaMemset2DAsync(R->d, size_t(R->ld) * 8, 0, size_t(R->rows) * 8, size_t(R->cols), ctx->stream));
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SS_OK;
+    }
+    ChainWs w;
+    SS_TRY(chain_front(ctx, Xs, Y, &w));
+    SS_TRY(launch_gemm_f64(ctx, SS_OP_N, Xq->d, Xq->ld, w.T, w.ldt, R->d, R->ld, Xq->rows, Y->cols, Xq->cols,
+                           nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, false));
+    if (kt_out)
+        SS_CHECK_CUDA(cudaMemcpyAsync(kt_out->d, w.kt, size_t(Y->cols) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Y && R, "ss_predict_source: null matrix");
+    SS_REQUIRE(!Xs || Xs->rows == Y->rows, "Labels and features have different number of source nodes");
+    SS_REQUIRE(R->rows == Y->rows && R->cols == Y->cols, "ss_predict_source: R must be Ns x Nt");
+    if (R->rows == 0 || R->cols == 0) return SS_OK;
+    const ss_mat* Xeff = (Xs && Xs->cols > 0) ? Xs : nullptr;
+    ChainWs w;
+    SS_TRY(chain_front(ctx, Xeff, Y, &w));
+    const int64_t ns = Y->rows, nt = Y->cols;
+    // U[t',t] = (sum_s Y[s,t'] * Wst[s,t]) / kt[t']
+    void* p;
+    const int64_t ldu = round_up(nt, 16);
+    SS_TRY(scratch_get(ctx, 3, size_t(ldu) * size_t(nt) * 8, &p));
+    double* U = static_cast<double*>(p);
+    SS_TRY(launch_gemm_f64(ctx, SS_OP_T, Y->d, Y->ld, w.Wst, w.ldw, U, ldu, nt, nt, ns, w.kt, nullptr, false));
+    const int32_t* flag = (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr;
+    if (Xeff) {
+        SS_TRY(launch_gemm_f64(ctx, SS_OP_N, Xeff->d, Xeff->ld, w.T, w.ldt, R->d, R->ld, ns, nt, Xeff->cols, nullptr,
+                               nullptr, false));
+        SS_TRY(launch_gemm_f64(ctx, SS_OP_N, Y->d, Y->ld, U, ldu, R->d, R->ld, ns, nt, nt, nullptr, flag, true));
+    } else {
+        SS_TRY(launch_gemm_f64(ctx, SS_OP_N, Y->d, Y->ld, U, ldu, R->d, R->ld, ns, nt, nt, nullptr, flag, false));
+    }
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(R && kt && kt->n == R->cols, "ss_clean: bad argument");
+    SS_TRY(launch_clean(ctx, R->d, R->rows, R->cols, R->ld, kt->d));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// Host-buffer form: Xs / Y are uploaded once, then query-row slabs of Xq stream in on copy_in while
+// the R GEMM of the previous slab runs on `stream` and finished R slabs stream out on copy_out.
+int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const double* Xs, int64_t ldxs,
+                              const double* Y, int64_t ldy, int64_t nq, int64_t ns, int64_t nf, int64_t nt,
+                              uint32_t flags, double* R, int64_t ldr) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(nq >= 0 && ns >= 0 && nf >= 0 && nt >= 0, "ss_predict_query_host: negative dimension");
+    SS_REQUIRE(ldxq >= nq && ldxs >= ns && ldy >= ns && ldr >= nq, "ss_predict_query_host: leading dimension too small");
+    if (nq == 0 || nt == 0) return SS_OK;
+    SS_REQUIRE(Xq && Xs && Y && R, "ss_predict_query_host: null buffer");
+    if (ns == 0 || nf == 0) {
+        for (int64_t c = 0; c < nt; ++c) memset(R + c * ldr, 0, size_t(nq) * 8);
+        return SS_OK;
+    }
+    // resident operands
+    ss_mat mXs, mY;
+    void* p;
+    mXs.ctx = mY.ctx = ctx;
+    mXs.rows = ns; mXs.cols = nf; mXs.ld = round_up(ns, 16);
+    mY.rows = ns; mY.cols = nt; mY.ld = round_up(ns, 16);
+    SS_TRY(scratch_get(ctx, 4, size_t(mXs.ld) * size_t(nf) * 8, &p));
+    mXs.d = static_cast<double*>(p);
+    SS_TRY(scratch_get(ctx, 5, size_t(mY.ld) * size_t(nt) * 8, &p));
+    mY.d = static_cast<double*>(p);
+    SS_TRY(copy2d(ctx, ctx->stream, mXs.d, mXs.ld, Xs, ldxs, ns, nf, cudaMemcpyHostToDevice));
+    SS_TRY(copy2d(ctx, ctx->stream, mY.d, mY.ld, Y, ldy, ns, nt, cudaMemcpyHostToDevice));
+    ChainWs w;
+    SS_TRY(chain_front(ctx, &mXs, &mY, &w));
+
+    // slab size: about 1 GiB of Xq+R per buffer, multiple of 128 rows
+    int64_t slab = (int64_t(1) << 30) / ((nf + nt) * 8);
+    slab = slab / 128 * 128;
+    if (slab < 128) slab = 128;
+    if (const char* env = getenv("SS_SLAB_ROWS")) {  // test hook: force many small slabs
+        const long long v = atoll(env);
+        if (v >= 16) slab = round_up(v, 16);
+    }
+    if (slab > nq) slab = round_up(nq, 16);
+    const int64_t nslab = ceil_div(nq, slab);
+    double* dXq[2];
+    double* dR[2];
+    SS_TRY(scratch_get(ctx, 6, size_t(slab) * size_t(nf) * 8 * 2, &p));
+    dXq[0] = static_cast<double*>(p);
+    dXq[1] = dXq[0] + slab * nf;
+    SS_TRY(scratch_get(ctx, 7, size_t(slab) * size_t(nt) * 8 * 2, &p));
+    dR[0] = static_cast<double*>(p);
+    dR[1] = dR[0] + slab * nt;
+    cudaEvent_t in_done[2], mm_done[2], out_done[2];
+    for (int i = 0; i < 2; ++i) {
+        SS_CHECK_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+        SS_CHECK_CUDA(cudaEventCreateWithFlags(&mm_done[i], cudaEventDisableTiming));
+        SS_CHECK_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+    }
+    int32_t status = SS_OK;
+    for (int64_t i = 0; i < nslab && status == SS_OK; ++i) {
+        const int b = int(i & 1);
+        const int64_t r0 = i * slab;
+        const int64_t nr = (nq - r0 < slab) ? nq - r0 : slab;
+        // upload slab i (needs the GEMM that last read this buffer to be done)
+        if (i >= 2) cudaStreamWaitEvent(ctx->copy_in, mm_done[b], 0);
+        status = copy2d(ctx, ctx->copy_in, dXq[b], slab, Xq + r0, ldxq, nr, nf, cudaMemcpyHostToDevice);
+        if (status != SS_OK) break;
+        cudaEventRecord(in_done[b], ctx->copy_in);
+        // GEMM slab i (needs its input and the download that last read this R buffer)
+        cudaStreamWaitEvent(ctx->stream, in_done[b], 0);
+        if (i >= 2) cudaStreamWaitEvent(ctx->stream, out_done[b], 0);
+        status = launch_gemm_f64(ctx, SS_OP_N, dXq[b], slab, w.T, w.ldt, dR[b], slab, nr, nt, nf, nullptr,
+                                 (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, false);
+        if (status != SS_OK) break;
+        cudaEventRecord(mm_done[b], ctx->stream);
+        // download slab i
+        cudaStreamWaitEvent(ctx->copy_out, mm_done[b], 0);
+        status = copy2d(ctx, ctx->copy_out, R + r0, ldr, dR[b], slab, nr, nt, cudaMemcpyDeviceToHost);
+        cudaEventRecord(out_done[b], ctx->copy_out);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_in);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->copy_out);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(in_done[i]);
+        cudaEventDestroy(mm_done[i]);
+        cudaEventDestroy(out_done[i]);
+    }
+    if (status != SS_OK) return status;
+    SS_CHECK_CUDA(e1);
+    SS_CHECK_CUDA(e2);
+    SS_CHECK_CUDA(e3);
+    return SS_OK;
+}
+
+// ---- (4) ranking / metrics ---------------------------------------------------------------------
+
+int32_t ss_topl_rows(ss_ctx* ctx, const ss_mat* R, int32_t L, ss_ivec* idx_out, ss_mat* val_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(R && idx_out, "ss_topl_rows: null argument");
+    SS_REQUIRE(L > 0 && L <= R->cols, "ss_topl_rows: L must be in 1..cols");
+    SS_REQUIRE(idx_out->n == int64_t(L) * R->rows, "ss_topl_rows: idx_out must hold L x rows entries");
+    SS_REQUIRE(!val_out || (val_out->rows == L && val_out->cols == R->rows), "ss_topl_rows: val_out must be L x rows");
+    SS_TRY(launch_topl(ctx, R->d, R->rows, R->cols, R->ld, L, idx_out->d, val_out ? val_out->d : nullptr,
+                       val_out ? val_out->ld : 0));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_atl(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t L, double* out2) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Ytrue && R && out2, "ss_atl: null argument");
+    SS_REQUIRE(Ytrue->rows == R->rows && Ytrue->cols == R->cols, "Number of predictions must match number of labels");
+    if (L <= 0) {
+        set_error("Please use a list length greater than 0 (L > 0)");
+        return SS_ERR_ASSERT;
+    }
+    if (R->cols <= L) {
+        set_error("Number of labels is less than length (L > y)");
+        return SS_ERR_ASSERT;
+    }
+    return atl(ctx, Ytrue, R, L, out2);
+}
+
+int32_t ss_auroc_auprc(ss_ctx* ctx, const void* labels_u8_dev, const void* scores_f64_dev, int64_t M, double* out2) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out2 && M >= 0 && (M == 0 || (labels_u8_dev && scores_f64_dev)), "ss_auroc_auprc: bad argument");
+    return auroc_auprc(ctx, static_cast<const uint8_t*>(labels_u8_dev), static_cast<const double*>(scores_f64_dev), M,
+                       out2);
+}
+
+int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, double* out2) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Ytrue && R && out2, "ss_auroc_auprc_mat: null argument");
+    if (Ytrue->rows != R->rows || Ytrue->cols != R->cols) {
+        set_error("The number of scores must be equal to the number of labels");
+        return SS_ERR_ASSERT;
+    }
+    return auroc_auprc_mat(ctx, Ytrue, R, out2);
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Shared internals of libsimspread_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/simspread_b200.h"
+
+namespace ss {
+
+void set_error(const char* fmt, ...);
+
+#define SS_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ss::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                          __LINE__);                                                          \
+            return (_e == cudaErrorMemoryAllocation) ? SS_ERR_OOM : SS_ERR_CUDA;              \
+        }                                                                                     \
+    } while (0)
+
+#define SS_REQUIRE(cond, ...)             \
+    do {                                  \
+        if (!(cond)) {                    \
+            ss::set_error(__VA_ARGS__);   \
+            return SS_ERR_INVALID;        \
+        }                                 \
+    } while (0)
+
+#define SS_TRY(expr)                 \
+    do {                             \
+        int32_t _s = (expr);         \
+        if (_s != SS_OK) return _s;  \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// grow-only device scratch buffer
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace ss
+
+struct ss_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t copy_in = nullptr;  // H2D pipeline
+    cudaStream_t copy_out = nullptr; // D2H pipeline
+    int64_t launches = 0;
+    // workspaces reused across predict calls (never shrink)
+    ss::Scratch ws[16];
+    int32_t* tile_counter = nullptr;
+    bool gemm_attr_set = false;
+    // optional per-GEMM timing (ss_ctx_profile)
+    bool profile = false;
+    struct ProfRec {
+        cudaEvent_t start, stop;
+        double flops;
+    };
+    std::vector<ProfRec> prof;
+};
+
+struct ss_mat {
+    ss_ctx* ctx = nullptr;
+    double* d = nullptr;
+    int64_t rows = 0, cols = 0, ld = 0;
+    bool owned = false;
+};
+
+struct ss_ivec {
+    ss_ctx* ctx = nullptr;
+    int32_t* d = nullptr;
+    int64_t n = 0;
+    bool owned = false;
+};
+
+struct ss_csr {
+    ss_ctx* ctx = nullptr;
+    int64_t rows = 0, cols = 0, nnz = 0;
+    int32_t* row_ptr = nullptr;  // rows + 1
+    int32_t* col_idx = nullptr;  // nnz
+    double* values = nullptr;    // nnz or null
+};
+
+namespace ss {
+
+int32_t scratch_get(ss_ctx* ctx, int slot, size_t bytes, void** out);
+
+// ---- kernels (launchers; all asynchronous on ctx->stream) --------------------------------------
+int32_t launch_featurize(ss_ctx* ctx, const double* S, int64_t rows, int64_t cols, int64_t lds,
+                         double alpha, bool weighted, double* X, int64_t ldx);
+int32_t launch_gather(ss_ctx* ctx, const double* src, int64_t lds, const int32_t* ridx,
+                      const int32_t* cidx, double* dst, int64_t rows, int64_t cols, int64_t ldd);
+int32_t launch_degrees(ss_ctx* ctx, const double* M, int64_t rows, int64_t cols, int64_t ld,
+                       int32_t* row_deg, int32_t* col_deg);  // accumulates into row_deg (+=)
+int32_t launch_spread_rows(ss_ctx* ctx, const double* G, int64_t rows, int64_t cols, int64_t ldg,
+                           const int32_t* k, double* W, int64_t ldw);
+int32_t launch_clean(ss_ctx* ctx, double* R, int64_t rows, int64_t cols, int64_t ld,
+                     const int32_t* kt);
+int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                        const int32_t* row_div, const int32_t* col_flag, bool accumulate);
+int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
+int32_t launch_topl(ss_ctx* ctx, const double* R, int64_t rows, int64_t cols, int64_t ld, int L,
+                    int32_t* idx_out, double* val_out, int64_t ldv);
+int32_t atl(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int L, double* out2);
+int32_t auroc_auprc(ss_ctx* ctx, const uint8_t* labels, const double* scores, int64_t M,
+                    double* out2);
+int32_t auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, double* out2);
+
+}  // namespace ss

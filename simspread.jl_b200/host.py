@@ -1,0 +1,618 @@
+"""Host-side mirror of SimSpread.jl's exported API for the resource-spreading path
+(reference src/SimSpread.jl:21-56), written in Python because Julia is not available in the build
+image; `julia/SimSpreadB200.jl` is the same layer in Julia over the same C ABI.
+
+Same names, argument meaning and error behaviour as the reference: `cutoff`, `cutoff_` (cutoff!),
+`featurize`, `featurize_` (featurize!), `k`, `construct`, `spread`, `predict`, `clean_` (clean!),
+`split`, `AuROC`, `AuPRC`, `recallatL`, `precisionatL`.  Index arguments that are 1-based in Julia
+(`k(v, G)`) are 1-based here too.  All array work is done by libsimspread_b200.so on the GPU; this
+module only does name bookkeeping (the NamedArrays part of the reference) and argument checks.
+There is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import SS_OP_N, SS_OP_T, SS_PREDICT_CLEAN, check, lib
+from .namedarray import NamedArray
+
+# ------------------------------------------------------------------------------------------------
+# device plumbing
+# ------------------------------------------------------------------------------------------------
+
+
+class Context:
+    """One GPU (`ss_ctx`).  `Context.default()` picks LOCAL_RANK (one process per GPU)."""
+
+    _default: Optional["Context"] = None
+
+    def __init__(self, device: Optional[int] = None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        check(lib().ss_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context()
+        return cls._default
+
+    def sync(self):
+        check(lib().ss_ctx_sync(self.h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(lib().ss_ctx_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib().ss_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def profile(self, enable: bool):
+        check(lib().ss_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self, cap: int = 4096):
+        """[(ms, flops)] of every chain-product GEMM launched since profile(True)."""
+        ms, fl, n = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int32()
+        check(lib().ss_ctx_profile_read(self.h, ms, fl, cap, C.byref(n)))
+        return [(ms[i], fl[i]) for i in range(n.value)]
+
+    def close(self):
+        if self.h:
+            lib().ss_ctx_destroy(self.h)
+            self.h = None
+
+
+def _f64_colmajor(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+class DMat:
+    """Device matrix handle (`ss_mat`), column-major float64."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int):
+        self.ctx = ctx
+        self.rows, self.cols = int(rows), int(cols)
+        h = C.c_void_p()
+        check(lib().ss_mat_create(ctx.h, self.rows, self.cols, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_host(cls, ctx: Context, a) -> "DMat":
+        a = _f64_colmajor(a)
+        m = cls(ctx, a.shape[0], a.shape[1])
+        if a.size:
+            check(lib().ss_mat_upload(ctx.h, m.h, a.ctypes.data, max(a.shape[0], 1)))
+        return m
+
+    @classmethod
+    def wrap(cls, ctx: Context, devptr: int, rows: int, cols: int, ld: int) -> "DMat":
+        m = cls.__new__(cls)
+        m.ctx, m.rows, m.cols = ctx, int(rows), int(cols)
+        h = C.c_void_p()
+        check(lib().ss_mat_wrap(ctx.h, C.c_void_p(devptr), m.rows, m.cols, int(ld), C.byref(h)))
+        m.h = h
+        return m
+
+    def info(self):
+        r, c, ld, p = C.c_int64(), C.c_int64(), C.c_int64(), C.c_void_p()
+        check(lib().ss_mat_info(self.h, C.byref(r), C.byref(c), C.byref(ld), C.byref(p)))
+        return r.value, c.value, ld.value, p.value
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty((self.rows, self.cols), dtype=np.float64, order="F")
+        if out.size:
+            check(lib().ss_mat_download(self.ctx.h, self.h, out.ctypes.data, max(self.rows, 1)))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().ss_mat_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class DIVec:
+    """Device int32 vector handle (`ss_ivec`)."""
+
+    def __init__(self, ctx: Context, n: int):
+        self.ctx, self.n = ctx, int(n)
+        h = C.c_void_p()
+        check(lib().ss_ivec_create(ctx.h, self.n, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_host(cls, ctx: Context, a) -> "DIVec":
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        v = cls(ctx, a.size)
+        if a.size:
+            check(lib().ss_ivec_upload(ctx.h, v.h, a.ctypes.data))
+        return v
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        if self.n:
+            check(lib().ss_ivec_download(self.ctx.h, self.h, out.ctypes.data))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().ss_ivec_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _h(x):
+    return x.h if x is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# graphs.jl : k
+# ------------------------------------------------------------------------------------------------
+
+
+def k(*args):
+    """`k(v, G)` (1-based row), `k(e::Vector)`, `k(G::Matrix)` -- reference src/graphs.jl:9-11.
+    `k(G)` returns an (n, 1) int64 column like `mapslices(k, G; dims=2)`."""
+    ctx = Context.default()
+    if len(args) == 2:
+        v, G = args
+        G = G.array if isinstance(G, NamedArray) else np.asarray(G)
+        return int(k(np.asarray(G)[int(v) - 1, :]))
+    (G,) = args
+    G = G.array if isinstance(G, NamedArray) else np.asarray(G)
+    if G.ndim == 1:  # one row
+        d = DMat.from_host(ctx, G.reshape(1, -1))
+        out = DIVec(ctx, 1)
+        check(lib().ss_k_rows(ctx.h, d.h, out.h))
+        return int(out.to_host()[0])
+    d = DMat.from_host(ctx, G)
+    out = DIVec(ctx, G.shape[0])
+    check(lib().ss_k_rows(ctx.h, d.h, out.h))
+    return out.to_host().astype(np.int64).reshape(-1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# core.jl : cutoff / featurize
+# ------------------------------------------------------------------------------------------------
+
+
+def _cutoff_array(X, alpha: float, weighted: bool) -> np.ndarray:
+    ctx = Context.default()
+    X = np.asarray(X)
+    shape = X.shape
+    d = DMat.from_host(ctx, X)
+    check(lib().ss_featurize(ctx.h, d.h, float(alpha), int(bool(weighted)), d.h))
+    return d.to_host().reshape(shape, order="F") if X.ndim == 1 else d.to_host()
+
+
+def cutoff(x, alpha, weighted: bool = False):
+    """reference src/core.jl:37-43 (scalar) and :55-60 (vector / matrix); default weighted=false.
+    The reference requires `typeof(x) == typeof(alpha)` (both AbstractFloat)."""
+    if np.isscalar(x):
+        if not isinstance(x, (float, np.floating)) or not isinstance(alpha, (float, np.floating)):
+            raise TypeError("MethodError: cutoff(x::T, alpha::T) needs AbstractFloat x and alpha")
+        return float(_cutoff_array(np.array([[x]], dtype=np.float64), alpha, weighted)[0, 0])
+    if not isinstance(alpha, (float, np.floating)):
+        raise TypeError("MethodError: cutoff(X::AbstractVecOrMat{T}, alpha::T) needs AbstractFloat alpha")
+    return _cutoff_array(x, alpha, weighted)
+
+
+def cutoff_(x, alpha, weighted: bool = False):
+    """`cutoff!` (reference src/core.jl:72-75, 87-89): despite the name the reference never
+    mutates its argument -- it only returns the transformed value.  Quirk kept."""
+    return cutoff(x, alpha, weighted)
+
+
+def featurize(X: NamedArray, alpha, weighted: bool = True) -> NamedArray:
+    """reference src/core.jl:106-112: threshold every entry (default weighted=true) and prefix the
+    column names with "f"."""
+    out = X.copy()
+    out.array = _cutoff_array(X.array, float(alpha), weighted)
+    out.setnames(["f" + f for f in out.names(2)], 2)
+    return out
+
+
+def featurize_(X: NamedArray, alpha, weighted: bool = True) -> None:
+    """`featurize!` (reference src/core.jl:129-132): in place."""
+    X.array = _cutoff_array(X.array, float(alpha), weighted)
+    X.setnames(["f" + f for f in X.names(2)], 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# core.jl : split
+# ------------------------------------------------------------------------------------------------
+
+
+def split(y: NamedArray, k_: int, seed: int = 1) -> List[List[str]]:
+    """reference src/core.jl:11-25: shuffle the source names, element i (1-based) -> fold
+    `mod(i, k) + 1`.  The shuffle uses NumPy's MT19937 stream, not Julia's MersenneTwister stream
+    (not reproducible outside Julia; the reference's own test is skipped, test/runtests.jl:34)."""
+    sources = y.names(1)
+    perm = np.random.RandomState(seed).permutation(len(sources))
+    groups: List[List[str]] = [[] for _ in range(k_)]
+    for i, j in enumerate(perm, start=1):
+        groups[i % k_].append(sources[j])  # mod(i,k)+1 in 1-based fold numbering
+    return groups
+
+
+# ------------------------------------------------------------------------------------------------
+# core.jl : construct
+# ------------------------------------------------------------------------------------------------
+
+
+class Graph:
+    """What `construct` returns in place of the reference's dense n x n NamedArray: the three
+    non-zero blocks (Xq = A[q,f], Xs = A[s,f], Y = A[s,t]) resident on the GPU plus the node names
+    in the reference's order (queries, sources, features, targets; src/core.jl:192-193).
+    `masked=True` is the `B` of the reference (query rows / columns zeroed, :196-198).  It still
+    satisfies the `(A, B)` protocol of `predict` and exposes `.names(d)` / `.array` (the dense
+    matrix, materialised on request for inspection only)."""
+
+    def __init__(self, ctx, queries, sources, features, targets, Xq: Optional[DMat], Xs: Optional[DMat],
+                 Y: DMat, masked: bool):
+        self.ctx = ctx
+        self.queries, self.sources = list(queries), list(sources)
+        self.features, self.targets = list(features), list(targets)
+        self.Xq, self.Xs, self.Y = Xq, Xs, Y
+        self.masked = masked
+
+    def names(self, d: Optional[int] = None):
+        n = [str(x) for x in self.queries + self.sources + self.features + self.targets]
+        return [n, list(n)] if d is None else n
+
+    @property
+    def array(self) -> np.ndarray:
+        nq, ns, nf, nt = len(self.queries), len(self.sources), len(self.features), len(self.targets)
+        n = nq + ns + nf + nt
+        A = np.zeros((n, n))
+        s0, f0, t0 = nq, nq + ns, nq + ns + nf
+        if nf:
+            Xs = self.Xs.to_host()
+            A[s0:f0, f0:t0] = Xs
+            A[f0:t0, s0:f0] = Xs.T
+            if nq and not self.masked:
+                Xq = self.Xq.to_host()
+                A[:nq, f0:t0] = Xq
+                A[f0:t0, :nq] = Xq.T
+        Y = self.Y.to_host()
+        A[s0:f0, t0:] = Y
+        A[t0:, s0:f0] = Y.T
+        return A
+
+    def to_named(self) -> NamedArray:
+        return NamedArray(self.array, self.names())
+
+
+def _assert_names_differ(features, sources, msg):
+    # reference: @assert all(sort(features) .!= sort(sources)) msg   (element-wise broadcast)
+    sf, ss = sorted(features), sorted(sources)
+    if len(sf) != len(ss):
+        raise ValueError("DimensionMismatch: arrays could not be broadcast to a common size; "
+                         f"got a dimension with lengths {len(sf)} and {len(ss)}")
+    assert all(a != b for a, b in zip(sf, ss)), msg
+
+
+def construct(*args):
+    """`construct(y, X, queries)` (reference src/core.jl:148-201), `construct((ytrain, ytest),
+    (Xtrain, Xtest))` (:217-276), `construct(ytrain, ytest, Xtrain, Xtest)` (:294-296) and the
+    3-layer `construct(y, X)` (:308-337)."""
+    if len(args) == 4:
+        return construct((args[0], args[1]), (args[2], args[3]))
+    if len(args) == 3:
+        y, X, queries = args
+        assert y.size(1) == X.size(1), "Labels and features have different number of source nodes"
+        queries = [str(q) for q in queries]
+        qset = set(queries)
+        features = [f for f in X.names(2) if f.lstrip("f") not in qset]
+        sources = [d for d in X.names(1) if d not in qset]
+        targets = y.names(2)
+        _assert_names_differ(features, sources, "Source and Features nodes have the same names!")
+        ctx = Context.default()
+        dX, dy = DMat.from_host(ctx, X.array), DMat.from_host(ctx, y.array)
+        qi = DIVec.from_host(ctx, X.index_of(queries, 1))
+        si = DIVec.from_host(ctx, X.index_of(sources, 1))
+        fi = DIVec.from_host(ctx, X.index_of(features, 2))
+        ysi = DIVec.from_host(ctx, y.index_of(sources, 1))
+        Xq, Xs = DMat(ctx, len(queries), len(features)), DMat(ctx, len(sources), len(features))
+        Y = DMat(ctx, len(sources), len(targets))
+        check(lib().ss_gather(ctx.h, dX.h, qi.h, fi.h, Xq.h))
+        check(lib().ss_gather(ctx.h, dX.h, si.h, fi.h, Xs.h))
+        check(lib().ss_gather(ctx.h, dy.h, ysi.h, None, Y.h))
+        A = Graph(ctx, queries, sources, features, targets, Xq, Xs, Y, masked=False)
+        B = Graph(ctx, queries, sources, features, targets, Xq, Xs, Y, masked=True)
+        return A, B
+    if len(args) == 2 and isinstance(args[0], tuple):
+        (ytrain, ytest), (Xtrain, Xtest) = args
+        assert ytrain.size(2) == ytest.size(2), \
+            "Number of targets between test and training sets doesn't match"
+        assert Xtrain.size(2) == Xtest.size(2), \
+            "Number of features between test and training sets doesn't match"
+        features, sources = Xtrain.names(2), ytrain.names(1)
+        targets, queries = ytrain.names(2), ytest.names(1)
+        _assert_names_differ(features, sources, "Features and drugs have the same names!")
+        ctx = Context.default()
+        Xq, Xs = DMat.from_host(ctx, Xtest.array), DMat.from_host(ctx, Xtrain.array)
+        Y = DMat.from_host(ctx, ytrain.array)
+        A = Graph(ctx, queries, sources, features, targets, Xq, Xs, Y, masked=False)
+        B = Graph(ctx, queries, sources, features, targets, Xq, Xs, Y, masked=True)
+        return A, B
+    if len(args) == 2:
+        y, X = args
+        features, sources, targets = X.names(2), y.names(1), y.names(2)
+        _assert_names_differ(features, sources, "Source and feature nodes have the same names")
+        ctx = Context.default()
+        Xs, Y = DMat.from_host(ctx, X.array), DMat.from_host(ctx, y.array)
+        return Graph(ctx, [], sources, features, targets, None, Xs, Y, masked=False)
+    raise TypeError("MethodError: no method matching construct(...)")
+
+
+# ------------------------------------------------------------------------------------------------
+# core.jl : spread / predict / clean!
+# ------------------------------------------------------------------------------------------------
+
+
+def spread(G):
+    """reference src/core.jl:365-380: `W = G ./ k(G)`, Inf -> 0, NaN -> 0.  Accepts a Float64 /
+    Bool matrix or a NamedArray (returns the same kind)."""
+    ctx = Context.default()
+    if isinstance(G, Graph):
+        G = G.to_named()
+    arr = G.array if isinstance(G, NamedArray) else np.asarray(G)
+    d = DMat.from_host(ctx, arr.astype(np.float64))
+    check(lib().ss_spread_rows(ctx.h, d.h, None, d.h))
+    W = d.to_host()
+    if isinstance(G, NamedArray):
+        out = G.copy()
+        out.array = W
+        return out
+    return W
+
+
+def _dense_predict(A: NamedArray, B: NamedArray, rows, cols) -> NamedArray:
+    """Literal reference path for arbitrary dense adjacency matrices: F = A * (W * W) with
+    W = spread(B) (src/core.jl:408-413), all three steps on the GPU."""
+    ctx = Context.default()
+    n = A.shape[0]
+    dA, dB = DMat.from_host(ctx, A.array), DMat.from_host(ctx, B.array)
+    check(lib().ss_spread_rows(ctx.h, dB.h, None, dB.h))  # dB <- W
+    W2, F = DMat(ctx, n, n), DMat(ctx, n, n)
+    check(lib().ss_gemm_f64(ctx.h, SS_OP_N, dB.h, dB.h, W2.h, None, None))
+    check(lib().ss_gemm_f64(ctx.h, SS_OP_N, dA.h, W2.h, F.h, None, None))
+    Fn = NamedArray(F.to_host(), A.names())
+    return Fn[list(rows), list(cols)]
+
+
+def predict(*args, GPU: bool = False, clean: bool = False) -> NamedArray:
+    """`predict((A, B), ytest)`, `predict(A, B, ytest)` (reference src/core.jl:402-425) and
+    `predict(A, ytrain)` (:446-466).  Returns `F[names(ytest,1), names(ytest,2)]`.
+
+    `GPU` is accepted for signature compatibility: this implementation always runs on the GPU, in
+    Float64 (the reference's GPU=true silently drops to Float32, src/core.jl:404).  `clean=True`
+    (extension) fuses `clean!` into the product's epilogue."""
+    ctx = Context.default()
+    if len(args) == 2 and isinstance(args[0], tuple):
+        (A, B), yq = args
+    elif len(args) == 3:
+        A, B, yq = args
+    elif len(args) == 2:
+        A, yq = args
+        B = A
+    else:
+        raise TypeError("MethodError: no method matching predict(...)")
+    rows, cols = yq.names(1), yq.names(2)
+    if not isinstance(A, Graph) or not isinstance(B, Graph):
+        An = A.to_named() if isinstance(A, Graph) else A
+        Bn = B.to_named() if isinstance(B, Graph) else B
+        return _dense_predict(An, Bn, rows, cols)
+    g = A
+    flags = SS_PREDICT_CLEAN if clean else 0
+    qpos = {n: i for i, n in enumerate(g.queries)}
+    spos = {n: i for i, n in enumerate(g.sources)}
+    tpos = {n: i for i, n in enumerate(g.targets)}
+    if not all(c in tpos for c in cols) or not all((r in qpos) or (r in spos) for r in rows):
+        # rows / columns outside the (query|source) x target block: literal dense path
+        return _dense_predict(A.to_named(), B.to_named(), rows, cols)
+    nt = len(g.targets)
+    out = np.empty((len(rows), len(cols)), order="F")
+    ci = [tpos[c] for c in cols]
+    want_q = [(i, qpos[r]) for i, r in enumerate(rows) if r in qpos]
+    want_s = [(i, spos[r]) for i, r in enumerate(rows) if r not in qpos]
+    if want_q:
+        if B is A and not B.masked:
+            # predict(A, y) with an unmasked 4-layer graph: W = spread(A) keeps the query rows;
+            # not the block-reduced form -- use the literal path
+            return _dense_predict(A.to_named(), A.to_named(), rows, cols)
+        R = DMat(ctx, len(g.queries), nt)
+        if len(g.features) and len(g.sources):
+            check(lib().ss_predict_query(ctx.h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, None))
+        Rh = R.to_host()
+        for i, qi in want_q:
+            out[i, :] = Rh[qi, ci]
+    if want_s:
+        R = DMat(ctx, len(g.sources), nt)
+        check(lib().ss_predict_source(ctx.h, _h(g.Xs) if len(g.features) else None, g.Y.h, R.h, flags))
+        Rh = R.to_host()
+        for i, si in want_s:
+            out[i, :] = Rh[si, ci]
+    return NamedArray(out, (rows, cols))
+
+
+def clean_(yhat: NamedArray, A, y: NamedArray) -> None:
+    """`clean!(yhat, A, y)` (reference src/core.jl:478-484): every target column whose node has
+    degree 0 in A is flagged with -99, in place."""
+    ctx = Context.default()
+    targets = y.names(2)
+    if isinstance(A, Graph):
+        kt = DIVec(ctx, len(A.targets))
+        check(lib().ss_degrees(ctx.h, None, A.Y.h, None, None, kt.h))
+        pos = {n: i for i, n in enumerate(A.targets)}
+        ktv = kt.to_host()[[pos[t] for t in targets]]
+    else:
+        rows = A[targets, A.names(2)]
+        ktv = k(rows.array).ravel()
+    dk = DIVec.from_host(ctx, ktv.astype(np.int32))
+    sub = yhat[yhat.names(1), targets]
+    d = DMat.from_host(ctx, sub.array)
+    check(lib().ss_clean(ctx.h, d.h, dk.h))
+    res = d.to_host()
+    ci = yhat.index_of(targets, 2)
+    yhat.array = np.array(yhat.array, dtype=np.float64)
+    yhat.array[:, ci] = res
+
+
+# ------------------------------------------------------------------------------------------------
+# performance.jl : ranking metrics
+# ------------------------------------------------------------------------------------------------
+
+
+def _auc_pair(y, yhat) -> Tuple[float, float]:
+    ctx = Context.default()
+    y = np.asarray(y).ravel()
+    yhat = np.asarray(yhat, dtype=np.float64).ravel()
+    assert len(y) == len(yhat), "The number of scores must be equal to the number of labels"
+    dy = DMat.from_host(ctx, (y != 0).astype(np.float64).reshape(-1, 1))
+    ds = DMat.from_host(ctx, yhat.reshape(-1, 1))
+    out = (C.c_double * 2)()
+    check(lib().ss_auroc_auprc_mat(ctx.h, dy.h, ds.h, out))
+    return float(out[0]), float(out[1])
+
+
+def AuROC(y, yhat) -> float:
+    """reference src/performance.jl:49-63."""
+    return _auc_pair(y, yhat)[0]
+
+
+def AuPRC(y, yhat) -> float:
+    """reference src/performance.jl:74-89."""
+    return _auc_pair(y, yhat)[1]
+
+
+def _atl(y, yhat, L: int) -> Tuple[float, float]:
+    """y, yhat: (groups, n) matrices; returns (mean recall@L, mean precision@L)."""
+    ctx = Context.default()
+    dy, ds = DMat.from_host(ctx, y), DMat.from_host(ctx, yhat)
+    out = (C.c_double * 2)()
+    check(lib().ss_atl(ctx.h, dy.h, ds.h, int(L), out))
+    return float(out[0]), float(out[1])
+
+
+def _atl_dispatch(which: int, y, yhat, *rest):
+    y = np.asarray(y, dtype=np.float64).ravel()
+    yhat = np.asarray(yhat, dtype=np.float64).ravel()
+    if len(rest) >= 1 and not np.isscalar(rest[0]):
+        grouping = np.asarray(rest[0]).ravel()
+        L = int(rest[1]) if len(rest) > 1 else 20
+        assert len(yhat) == len(grouping), "Number of groups must match number of predictions"
+        assert len(y) == len(grouping), "Number of groups must match number of labels"
+        assert len(y) == len(yhat), "Number of predictions must match number of labels"
+        assert L > 0, "Please use a list length greater than 0 (L > 0)"
+        order, seen = [], set()
+        for gname in grouping.tolist():
+            if gname not in seen:
+                seen.add(gname)
+                order.append(gname)
+        masks = [grouping == gname for gname in order]
+        sizes = {int(m.sum()) for m in masks}
+        if len(sizes) == 1:  # rectangular: one launch for all groups
+            Ym = np.stack([y[m] for m in masks])
+            Sm = np.stack([yhat[m] for m in masks])
+            return _atl(Ym, Sm, L)[which]
+        vals = [_atl(y[m].reshape(1, -1), yhat[m].reshape(1, -1), L)[which] for m in masks]
+        return float(np.sum(vals) / len(vals))
+    L = int(rest[0]) if rest else 20
+    assert L > 0, "Please use a list length greater than 0 (L > 0)"
+    assert len(y) == len(yhat), "Number of predictions and labels don't match"
+    return _atl(y.reshape(1, -1), yhat.reshape(1, -1), L)[which]
+
+
+def recallatL(y, yhat, *rest) -> float:
+    """`recallatL(y, yhat, L=20)` / `recallatL(y, yhat, grouping, L=20)` (reference
+    src/performance.jl:308-328, 341-357)."""
+    return _atl_dispatch(0, y, yhat, *rest)
+
+
+def precisionatL(y, yhat, *rest) -> float:
+    """`precisionatL(y, yhat, L=20)` / `precisionatL(y, yhat, grouping, L=20)` (reference
+    src/performance.jl:370-385, 398-414)."""
+    return _atl_dispatch(1, y, yhat, *rest)
+
+
+def validity_ratio(yhat) -> float:
+    """reference src/performance.jl:558-560: `sum(!iszero, yhat) / length(yhat)`."""
+    yhat = np.asarray(yhat, dtype=np.float64).ravel()
+    return int(k(yhat)) / yhat.size
+
+
+# ---- confusion-matrix scalars: O(1) host arithmetic in the reference as well ------
+
+_FLOATMIN = 2.2250738585072014e-308
+
+
+def _chk(tn, fp, fn, tp):
+    assert tn + fp + fn + tp > 0, "Confusion matrix sums zero!"
+
+
+def f1score(tn, fp, fn, tp):
+    _chk(tn, fp, fn, tp)
+    den = tp + 0.5 * (fp + fn)
+    return float("nan") if den == 0 else tp / den
+
+
+def mcc(*a):
+    """`mcc(a, b, eps=floatmin)` (reference src/performance.jl:150-152) or `mcc(tn, fp, fn, tp)`
+    (:170-200)."""
+    if len(a) in (2, 3):
+        x, y = a[0], a[1]
+        e = a[2] if len(a) == 3 else _FLOATMIN
+        return (x * e - y * e) / np.sqrt((x + y) * (x + e) * (y + e) * (e + e))
+    tn, fp, fn, tp = a
+    _chk(tn, fp, fn, tp)
+    p_pred, n_pred, p_act, n_act = tp + fp, fn + tn, tp + fn, fp + tn
+    if p_pred == 0:
+        return mcc(tn, fn)
+    if n_pred == 0:
+        return mcc(tp, fp)
+    if p_act == 0:
+        return mcc(tn, fp)
+    if n_act == 0:
+        return mcc(tp, fn)
+    return ((tp * tn) - (fp * fn)) / np.sqrt(float(p_pred) * n_pred * p_act * n_act)
+
+
+def accuracy(tn, fp, fn, tp):
+    _chk(tn, fp, fn, tp)
+    den = (tp + tn) + (fp + fn)
+    return float("nan") if den == 0 else (tp + tn) / den
+
+
+def balancedaccuracy(tn, fp, fn, tp):
+    _chk(tn, fp, fn, tp)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float((np.float64(tp) / np.float64(tp + fn) + np.float64(tn) / np.float64(tn + fp)) / 2)
+
+
+def recall(tn, fp, fn, tp):
+    _chk(tn, fp, fn, tp)
+    return float("nan") if tp + fn == 0 else tp / (tp + fn)
+
+
+def precision(tn, fp, fn, tp):
+    _chk(tn, fp, fn, tp)
+    return float("nan") if tp + fp == 0 else tp / (tp + fp)

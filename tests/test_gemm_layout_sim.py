@@ -1,0 +1,171 @@
+"""CPU replay of the index math of simspread.jl_b200/csrc/ss_gemm.cu (no GPU needed).
+
+The DMMA kernel reads its operands from TMA SWIZZLE_128B tiles with permuted k / row assignments
+so that every LDS.128 is bank-conflict free.  This test re-derives, in NumPy, (i) where TMA puts
+every element, (ii) which shared-memory address every lane reads, (iii) what mma.m8n8k4 computes
+from those fragments and (iv) where the epilogue stores each accumulator -- and checks the result
+against A @ B, plus the conflict-freeness of each warp-wide LDS.128.  It pins the *design*; the
+`-m gpu` tests pin the compiled kernel."""
+import numpy as np
+import pytest
+
+BM = BN = 128
+BK = 16
+WARPS_N = 4
+WM, WN = 64, 32
+MT, NT = WM // 8, WN // 8
+
+
+def swz(o):
+    return o ^ (((o >> 7) & 7) << 4)
+
+
+def rho(g):
+    return (g >> 1) | ((g & 1) << 2)
+
+
+def tma_kmajor(tile):
+    """tile[row, k] (128 x 16) -> 16 KB smem image, box {16 k, 128 rows}, 128B swizzle."""
+    sm = np.full(128 * 16, np.nan)
+    for r in range(128):
+        for k in range(16):
+            sm[swz(r * 128 + k * 8) // 8] = tile[r, k]
+    return sm
+
+
+def tma_mmajor(tile):
+    """tile[m, k] (128 x 16) -> 8 boxes {16 m, 16 k} of 2 KB each."""
+    sm = np.full(128 * 16, np.nan)
+    for b in range(8):
+        for k in range(16):
+            for mi in range(16):
+                o = k * 128 + mi * 8
+                sm[(b * 2048 + swz(o)) // 8] = tile[b * 16 + mi, k]
+    return sm
+
+
+def lds128(sm, addr, log):
+    assert addr % 16 == 0
+    log.append(addr)
+    return sm[addr // 8], sm[addr // 8 + 1]
+
+
+def check_conflicts(addrs):
+    """addrs: 32 lane byte addresses of one LDS.128; quarter-warps must hit 8 distinct 16B bank
+    groups (or identical addresses)."""
+    for q in range(4):
+        seen = {}
+        for a in addrs[8 * q:8 * q + 8]:
+            bank = (a >> 4) & 7
+            assert seen.setdefault(bank, a) == a, f"bank conflict in quarter {q}: {addrs}"
+
+
+def mma_8x8x4(acc, a, b):
+    """acc[lane][2], a[lane], b[lane] with lane = 4g+t: A[g][t], B[t][g(col)], C[g][2t+e]."""
+    A = a.reshape(8, 4)
+    B = b.reshape(8, 4).T  # B[t][col]
+    C = A @ B  # 8 x 8
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        acc[lane][0] += C[g, 2 * t]
+        acc[lane][1] += C[g, 2 * t + 1]
+
+
+def run_warp(sA, sB, warp, a_mmajor):
+    m_warp = (warp // WARPS_N) * WM
+    n_warp = (warp % WARPS_N) * WN
+    acc = np.zeros((MT, NT, 32, 2))
+    for h in range(2):
+        bf = np.zeros((NT, 32, 2))
+        for j in range(NT):
+            log = []
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                rg = rho(g)
+                off = (n_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4)
+                bf[j, lane] = lds128(sB, off + j * 8 * 128, log)
+            check_conflicts(log)
+        if a_mmajor:
+            for s2 in range(2):
+                s = 2 * h + s2
+                af = np.zeros((MT // 2, 32, 2))
+                for b in range(MT // 2):
+                    log = []
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        k = 2 * t + (s & 1) + 8 * (s >> 1)
+                        off = (m_warp >> 4) * 2048 + k * 128 + ((g ^ (k & 7)) << 4)
+                        af[b, lane] = lds128(sA, off + b * 2048, log)
+                    check_conflicts(log)
+                for b in range(MT // 2):
+                    for j in range(NT):
+                        mma_8x8x4(acc[2 * b, j], af[b, :, 0], bf[j, :, s2])
+                        mma_8x8x4(acc[2 * b + 1, j], af[b, :, 1], bf[j, :, s2])
+        else:
+            af = np.zeros((MT, 32, 2))
+            for i in range(MT):
+                log = []
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    rg = rho(g)
+                    off = (m_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4)
+                    af[i, lane] = lds128(sA, off + i * 8 * 128, log)
+                check_conflicts(log)
+            for s2 in range(2):
+                for i in range(MT):
+                    for j in range(NT):
+                        mma_8x8x4(acc[i, j], af[i, :, s2], bf[j, :, s2])
+    return acc
+
+
+def epilogue(C, acc, warp, a_mmajor):
+    m_warp = (warp // WARPS_N) * WM
+    n_warp = (warp % WARPS_N) * WN
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        for j in range(NT):
+            for e in range(2):
+                col = n_warp + 8 * j + t + 4 * e
+                if a_mmajor:
+                    for b in range(MT // 2):
+                        row = m_warp + 16 * b + 2 * g
+                        C[row, col] += acc[2 * b, j, lane, e]
+                        C[row + 1, col] += acc[2 * b + 1, j, lane, e]
+                else:
+                    for i in range(MT):
+                        C[m_warp + 8 * i + rho(g), col] += acc[i, j, lane, e]
+
+
+@pytest.mark.parametrize("a_mmajor", [True, False])
+def test_fragment_layout_reproduces_gemm(a_mmajor):
+    rng = np.random.default_rng(3)
+    K = 32
+    A = rng.integers(-4, 5, size=(BM, K)).astype(float)
+    B = rng.integers(-4, 5, size=(K, BN)).astype(float)
+    C = np.zeros((BM, BN))
+    for kb in range(K // BK):
+        At = A[:, kb * BK:(kb + 1) * BK]
+        Bt = B[kb * BK:(kb + 1) * BK, :].T  # [n, k]
+        sA = tma_mmajor(At) if a_mmajor else tma_kmajor(At)
+        sB = tma_kmajor(Bt)
+        for warp in range(8):
+            acc = run_warp(sA, sB, warp, a_mmajor)
+            epilogue(C, acc, warp, a_mmajor)
+    assert np.array_equal(C, A @ B)
+
+
+def test_tile_rasterisation_is_a_bijection():
+    GROUP_M = 16
+
+    def coord(tile, tiles_m, tiles_n):
+        gs = GROUP_M * tiles_n
+        gid = tile // gs
+        first = gid * GROUP_M
+        gm = min(tiles_m - first, GROUP_M)
+        r = tile - gid * gs
+        return first + r % gm, r // gm
+
+    for tm, tn in [(1, 1), (1, 6), (7, 3), (16, 5), (37, 11), (782, 391)]:
+        seen = {coord(t, tm, tn) for t in range(tm * tn)}
+        assert len(seen) == tm * tn
+        assert all(0 <= a < tm and 0 <= b < tn for a, b in seen)

@@ -1,0 +1,431 @@
+"""`-m gpu` parity tests: the CUDA path (through the C ABI / the host mirror of the reference API)
+against the CPU oracle on the same seeded inputs, and against the reference's golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact for thresholds, CSR indices, degrees and top-L order;
+<= 1e-12 relative error for FP64 scores."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # FP64 score tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def ss():
+    import simspread_b200 as m
+    m.build()
+    m.Context.default()  # raises without a B200: no CPU fallback
+    return m
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import simspread_oracle
+    return simspread_oracle
+
+
+def relerr(got, want):
+    """Element-wise relative error (all operands of the path are non-negative, so there is no
+    cancellation); entries whose expected value is exactly 0 must be exactly 0."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    zero = want == 0
+    if np.any(got[zero] != 0):
+        return float("inf")
+    if zero.all():
+        return 0.0
+    return float(np.max(np.abs(got[~zero] - want[~zero]) / np.abs(want[~zero])))
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the reference test-suite, through the API mirror
+# ---------------------------------------------------------------------------------------------
+
+
+def test_kat_k(ss, kats):
+    M = np.array(kats["k"]["M"], dtype=float)
+    assert ss.k(1, M) == 0
+    assert ss.k(M[0, :]) == 0
+    assert ss.k(M).ravel().tolist() == kats["k"]["expect"]
+    assert ss.k(M).shape == (4, 1)
+    assert ss.k(np.array([0.0, -0.0, np.nan, 1.0])) == 2
+
+
+def test_kat_cutoff_and_featurize(ss, kats):
+    c = kats["cutoff"]
+    x, y, z = c["x"], np.array(c["y"]).reshape(-1, 1), np.array(c["z"])
+    for case in c["cases"]:
+        a = case["alpha"]
+        assert ss.cutoff(x, a, False) == case["x_bin"]
+        assert ss.cutoff(x, a, True) == case["x_w"]
+        yw = y.ravel() if case["y_w"] == "y" else np.array(case["y_w"], dtype=float)
+        zw = z if case["z_w"] == "z" else np.array(case["z_w"], dtype=float)
+        assert np.array_equal(ss.cutoff(y, a, False).ravel(), np.array(case["y_bin"], dtype=float))
+        assert np.array_equal(ss.cutoff(y, a, True).ravel(), yw)
+        assert np.array_equal(ss.cutoff(z, a, False), np.array(case["z_bin"], dtype=float))
+        assert np.array_equal(ss.cutoff(z, a, True), zw)
+    zz = z.copy()
+    ss.cutoff_(zz, 0.5, False)
+    assert np.array_equal(zz, z)  # cutoff! does not mutate (reference quirk)
+    f = kats["featurize"]
+    M0 = ss.NamedArray(np.array(f["M0"]), (f["names"], f["names"]))
+    b, w = ss.featurize(M0, f["alpha"], False), ss.featurize(M0, f["alpha"], True)
+    assert np.array_equal(b.array, np.array(f["bin"], dtype=float)) and b.names(2) == f["colnames"]
+    assert np.array_equal(w.array, np.array(f["w"], dtype=float))
+    assert M0.names(2) == f["names"]  # featurize is not in place
+    ss.featurize_(M0, f["alpha"], False)
+    assert np.array_equal(M0.array, np.array(f["bin"], dtype=float)) and M0.names(2) == f["colnames"]
+
+
+def test_kat_construct(ss, kats, o):
+    c = kats["construct"]
+    X = ss.NamedArray(np.array(c["X"], dtype=float), (c["xrows"], c["xcols"]))
+    y = ss.NamedArray(np.array(c["y"], dtype=float), (c["xrows"], c["ycols"]))
+    A, B = ss.construct(y, X, c["queries"])
+    assert A.names(1) == A.names(2) == c["names"]
+    assert B.names(1) == B.names(2) == c["names"]
+    Ao, Bo, _ = o.construct_queries(y.array, (c["xrows"], c["ycols"]), X.array, (c["xrows"], c["xcols"]),
+                                    c["queries"])
+    assert np.array_equal(A.array, Ao) and np.array_equal(B.array, Bo)
+
+
+def test_kat_spread(ss, kats):
+    s = kats["spread"]
+    W = ss.spread(np.array(s["M"], dtype=float))
+    assert np.array_equal(W, np.array([[1, 0, 0], [.5, .5, 0], [1 / 3, 1 / 3, 1 / 3]]))
+    assert np.array_equal(ss.spread(np.zeros((3, 3))), np.zeros((3, 3)))  # 0/0 -> NaN -> 0
+
+
+def test_kat_predict_exact(ss, kats):
+    p = kats["predict"]
+    A = ss.NamedArray(np.array(p["A"], dtype=float), (p["names"], p["names"]))
+    B = ss.NamedArray(np.array(p["B"], dtype=float), (p["names"], p["names"]))
+    y = ss.NamedArray(np.array([[0., 1.]]), (p["rows"], p["cols"]))
+    want = np.array(p["yhat"])
+    assert np.array_equal(ss.predict(A, B, y).array, want)      # exact ==, as the reference test
+    assert np.array_equal(ss.predict((A, B), y).array, want)
+    # same graph through construct (block-reduced path)
+    Xt = ss.NamedArray(A.array[0:1, 4:7], (["q1"], ["f1", "f2", "f3"]))
+    Xs = ss.NamedArray(A.array[1:4, 4:7], (["s1", "s2", "s3"], ["f1", "f2", "f3"]))
+    ys = ss.NamedArray(A.array[1:4, 7:9], (["s1", "s2", "s3"], ["t1", "t2"]))
+    G = ss.construct(ys, y, Xs, Xt)
+    assert np.array_equal(G[0].array, A.array) and np.array_equal(G[1].array, B.array)
+    assert np.array_equal(ss.predict(G, y).array, want)
+
+
+def test_kat_clean(ss, kats):
+    c = kats["clean"]
+    A = ss.NamedArray(np.array(c["A"], dtype=float), (c["names"], c["names"]))
+    yhat = ss.NamedArray(np.array(c["yhat"], dtype=float), (["q1"], c["targets"]))
+    y = ss.NamedArray(np.array([[0., 1.]]), (["q1"], c["targets"]))
+    ss.clean_(yhat, A, y)
+    assert np.array_equal(yhat.array, np.array(c["expect"], dtype=float))
+
+
+def test_kat_atL(ss, kats):
+    a = kats["atL"]
+    for L, v in a["recall"].items():
+        assert ss.recallatL(a["y"], a["yhat"], a["grouping"], int(L)) == pytest.approx(v, rel=1e-15)
+    for L, v in a["precision"].items():
+        assert ss.precisionatL(a["y"], a["yhat"], a["grouping"], int(L)) == pytest.approx(v, rel=1e-15)
+    with pytest.raises(AssertionError, match="Number of labels is less than length"):
+        ss.recallatL(a["y"], a["yhat"], 10)
+    assert math.isnan(ss.recallatL([0, 0, 1, 0], [1, 2, 3, 4], [1, 1, 2, 2], 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels against the oracle
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 5), (445, 445), (1000, 333), (2049, 130)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_featurize_dense_and_csr_bit_exact(ss, o, rows, cols, weighted):
+    rng = np.random.default_rng(rows * 1000 + cols)
+    S = np.round(rng.random((rows, cols)), 3)
+    S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = np.nan
+    S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = -0.0
+    S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = 0.35  # exactly alpha: kept (>=)
+    for alpha in (0.35, -0.01, 0.0, 1.01):
+        want = o.cutoff(S, alpha, weighted)
+        got = ss.cutoff(S, alpha, weighted)
+        assert np.array_equal(got, want)
+        assert np.array_equal(np.signbit(got), np.signbit(want))
+        # CSR (warp-ballot compaction)
+        ctx = ss.Context.default()
+        d = ss.DMat.from_host(ctx, S)
+        h = C.c_void_p()
+        from simspread_b200._lib import check
+        check(ss.lib().ss_featurize_csr(ctx.h, d.h, alpha, int(weighted), C.byref(h)))
+        r, c, nnz, hv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        check(ss.lib().ss_csr_info(h, C.byref(r), C.byref(c), C.byref(nnz), C.byref(hv)))
+        rp = np.empty(rows + 1, np.int32)
+        ci = np.empty(max(nnz.value, 1), np.int32)
+        va = np.empty(max(nnz.value, 1), np.float64)
+        check(ss.lib().ss_csr_download(ctx.h, h, rp.ctypes.data, ci.ctypes.data, va.ctypes.data if hv.value else None))
+        ss.lib().ss_csr_destroy(h)
+        wr, wc = np.nonzero(want != 0)  # row-major order == CSR order
+        assert nnz.value == len(wr) and bool(hv.value) == weighted
+        assert np.array_equal(rp, np.concatenate(([0], np.cumsum(np.bincount(wr, minlength=rows)))).astype(np.int32))
+        assert np.array_equal(ci[:nnz.value], wc.astype(np.int32))
+        if weighted:
+            assert np.array_equal(va[:nnz.value], want[wr, wc])
+
+
+@pytest.mark.parametrize("ns,nf,nt", [(1, 1, 1), (13, 13, 5), (401, 401, 664), (1500, 700, 129)])
+def test_degrees_exact(ss, o, ns, nf, nt):
+    rng = np.random.default_rng(ns + nf + nt)
+    Xs = o.cutoff(np.round(rng.random((ns, nf)), 3), 0.6, True)
+    Xs.flat[rng.integers(0, Xs.size, size=max(1, Xs.size // 40))] = np.nan
+    Xs.flat[rng.integers(0, Xs.size, size=max(1, Xs.size // 40))] = -0.0
+    Y = (rng.random((ns, nt)) < 0.05).astype(float)
+    ks, kf, kt = o.degrees_blocks(Xs, Y)
+    ctx = ss.Context.default()
+    dX, dY = ss.DMat.from_host(ctx, Xs), ss.DMat.from_host(ctx, Y)
+    vs, vf, vt = ss.DIVec(ctx, ns), ss.DIVec(ctx, nf), ss.DIVec(ctx, nt)
+    from simspread_b200._lib import check
+    check(ss.lib().ss_degrees(ctx.h, dX.h, dY.h, vs.h, vf.h, vt.h))
+    assert np.array_equal(vs.to_host(), ks) and np.array_equal(vf.to_host(), kf) and np.array_equal(vt.to_host(), kt)
+    assert np.array_equal(ss.k(Xs).ravel(), o.k_mat(Xs).ravel())
+    # spread on the same matrix: W = G ./ k(G), NaN/Inf -> 0 -- element-wise identical to IEEE division
+    G = np.where(np.isnan(Xs), 2.5, Xs)
+    assert np.array_equal(ss.spread(G), o.spread(G))
+
+
+GEMM_SHAPES = [(1, 1, 1), (5, 3, 2), (128, 128, 16), (129, 127, 17), (300, 200, 100), (45, 664, 400),
+               (1000, 37, 555), (64, 1500, 1031)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("op", ["N", "T"])
+def test_gemm_f64_against_numpy(ss, M, N, K, op):
+    from simspread_b200._lib import SS_OP_N, SS_OP_T, check
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    ctx = ss.Context.default()
+    for integer in (True, False):
+        if integer:  # sums exactly representable -> bit-exact regardless of summation order
+            A = rng.integers(-3, 4, size=(M, K)).astype(float)
+            B = rng.integers(-3, 4, size=(K, N)).astype(float)
+        else:
+            A, B = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+        dA = ss.DMat.from_host(ctx, A if op == "N" else A.T)
+        dB, dC = ss.DMat.from_host(ctx, B), ss.DMat(ctx, M, N)
+        check(ss.lib().ss_gemm_f64(ctx.h, SS_OP_N if op == "N" else SS_OP_T, dA.h, dB.h, dC.h, None, None))
+        got, want = dC.to_host(), A @ B
+        if integer:
+            assert np.array_equal(got, want)
+        else:
+            bound = np.abs(A) @ np.abs(B)  # forward error bound scale of a K-term dot product
+            assert np.max(np.abs(got - want) / np.maximum(bound, 1e-300)) < 1e-13
+        # fused epilogues: row division (k == 0 -> 0) and clean! flag
+        div = rng.integers(0, 4, size=M).astype(np.int32)
+        flag = rng.integers(0, 2, size=N).astype(np.int32)
+        dd, df = ss.DIVec.from_host(ctx, div), ss.DIVec.from_host(ctx, flag)
+        check(ss.lib().ss_gemm_f64(ctx.h, SS_OP_N if op == "N" else SS_OP_T, dA.h, dB.h, dC.h, dd.h, df.h))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref = np.where(div[:, None] == 0, 0.0, got / div[:, None].astype(float))
+        ref[:, flag == 0] = -99.0
+        assert np.array_equal(dC.to_host(), ref)
+
+
+def _enzyme_like(o, seed=20241):
+    """BASELINE config 2 shape: 445 drugs x 664 targets, binary alpha-cutoff features."""
+    rng = np.random.default_rng(seed)
+    N, Nt = 445, 664
+    S = np.round(rng.beta(2, 5, size=(N, N)), 6)
+    np.fill_diagonal(S, 1.0)
+    Y = (rng.random((N, Nt)) < 0.0099).astype(float)
+    return S, Y
+
+
+@pytest.mark.parametrize("weighted,alpha", [(False, 0.35), (True, 0.2), (True, 0.0)])
+def test_predict_cv_fold_against_oracle(ss, o, weighted, alpha):
+    S, Yfull = _enzyme_like(o)
+    N, Nt = Yfull.shape
+    names = [f"D{i:04d}" for i in range(N)]
+    tnames = [f"T{j:04d}" for j in range(Nt)]
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Yfull, (names, tnames))
+    X = ss.featurize(DD, alpha, weighted)
+    Xo, xr, xc = o.featurize(S, names, names, alpha, weighted)
+    assert np.array_equal(X.array, Xo) and X.names(2) == xc
+    folds = ss.split(DT, 10, seed=1)
+    assert sorted(sum(folds, [])) == sorted(names)
+    for queries in folds[:3]:
+        A, B = ss.construct(DT, X, queries)
+        ytest = DT[queries, tnames]
+        yhat = ss.predict((A, B), ytest)
+        Ao, Bo, nn = o.construct_queries(Yfull, (names, tnames), Xo, (xr, xc), queries)
+        assert A.names(1) == nn
+        want = o.predict_dense(Ao, Bo, nn, queries, tnames)  # literal n x n reference path
+        assert yhat.names(1) == queries and yhat.names(2) == tnames
+        assert relerr(yhat.array, want) < RTOL
+        # clean!: fused flag == separate call == oracle
+        want_c = want.copy()
+        o.clean(want_c, Ao, nn, tnames)
+        fused = ss.predict((A, B), ytest, clean=True)
+        ss.clean_(yhat, A, ytest)
+        assert relerr(yhat.array, want_c) < RTOL and np.array_equal(yhat.array == -99, want_c == -99)
+        assert np.array_equal(fused.array, yhat.array)
+        # training rows through the same graph (tutorial usage, src/core.jl:421 with source names)
+        some = A.sources[:25]
+        ytr = DT[some, tnames]
+        assert relerr(ss.predict((A, B), ytr).array, o.predict_dense(Ao, Bo, nn, some, tnames)) < RTOL
+
+
+def test_predict_three_layer_and_two_layer(ss, o, iris):
+    S, Cc, names = iris["S"], iris["C"], iris["names"]
+    X = ss.featurize(ss.NamedArray(S, (names, names)), 0.9, True)
+    y = ss.NamedArray(Cc, (names, iris["classes"]))
+    A = ss.construct(y, X)
+    got = ss.predict(A, y)
+    Ao, nn = o.construct_3layer(Cc, (names, iris["classes"]), X.array, (names, X.names(2)))
+    assert A.names(1) == nn
+    want = o.predict_dense_single(Ao, nn, names, iris["classes"])
+    assert relerr(got.array, want) < RTOL
+    # time-split form on iris (tutorial): 15 queries
+    q = names[::10]
+    tr = [n for n in names if n not in q]
+    Xn = ss.NamedArray(S, (names, names))
+    Xtr, Xte = ss.featurize(Xn[tr, tr], 0.9, True), ss.featurize(Xn[q, tr], 0.9, True)
+    G = ss.construct(y[tr, iris["classes"]], y[q, iris["classes"]], Xtr, Xte)
+    got = ss.predict(G, y[q, iris["classes"]])
+    Ao, Bo, nn = o.construct_split(Cc[[names.index(t) for t in tr]], (tr, iris["classes"]),
+                                   Cc[[names.index(t) for t in q]], (q, iris["classes"]),
+                                   Xtr.array, (tr, Xtr.names(2)), Xte.array, (q, Xte.names(2)))
+    want = o.predict_dense(Ao, Bo, nn, q, iris["classes"])
+    assert relerr(got.array, want) < RTOL
+    assert ss.AuROC(Cc[[names.index(t) for t in q]].ravel() > 0, got.array.ravel()) == pytest.approx(
+        o.AuROC(Cc[[names.index(t) for t in q]].ravel() > 0, want.ravel()), rel=1e-12)
+
+
+@pytest.mark.parametrize("nq,ns,nf,nt,slab", [(700, 300, 260, 190, 128), (33, 50, 40, 20, 16), (1, 3, 3, 2, 0)])
+def test_predict_query_host_pipelined(ss, o, nq, ns, nf, nt, slab):
+    """The reference-facing host-buffer entry point (slabs of query rows streamed through)."""
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=5, y_density=0.05, alpha=0.3, weighted=True)
+    Y[:, 1 % nt] = 0.0
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    ctx = ss.Context.default()
+    if slab:
+        os.environ["SS_SLAB_ROWS"] = str(slab)
+    try:
+        R = np.full((nq + 3, nt), 7.0, order="F")  # ld > rows: padding must stay untouched
+        check(ss.lib().ss_predict_query_host(ctx.h, Xq.ctypes.data, nq, Xs.ctypes.data, ns, Y.ctypes.data, ns,
+                                             nq, ns, nf, nt, SS_PREDICT_CLEAN, R.ctypes.data, nq + 3))
+    finally:
+        os.environ.pop("SS_SLAB_ROWS", None)
+    assert relerr(R[:nq], want) < RTOL
+    assert np.array_equal(R[:nq] == -99, want == -99)
+    assert np.all(R[nq:] == 7.0)
+
+
+def test_empty_and_degenerate_inputs(ss, o):
+    from simspread_b200._lib import check
+    ctx = ss.Context.default()
+    # no edges at all: every degree is 0 -> W = 0 -> scores 0, every column flagged by clean!
+    Xq, Xs, Y = np.ones((4, 3)), np.zeros((5, 3)), np.zeros((5, 2))
+    dq, dx, dy, R = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y, np.ones((4, 2))))
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, 0, None))
+    assert np.array_equal(R.to_host(), np.zeros((4, 2)))
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, 1, None))
+    assert np.array_equal(R.to_host(), np.full((4, 2), -99.0))
+    # zero queries / zero-size matrices are accepted
+    e = ss.DMat(ctx, 0, 3)
+    R0 = ss.DMat(ctx, 0, 2)
+    check(ss.lib().ss_predict_query(ctx.h, e.h, dx.h, dy.h, R0.h, 0, None))
+    assert ss.cutoff(np.zeros((0, 4)), 0.5).shape == (0, 4)
+    # shape errors carry the reference's assertion text
+    bad = ss.DMat(ctx, 4, 2)
+    st = ss.lib().ss_predict_query(ctx.h, bad.h, dx.h, dy.h, R.h, 0, None)
+    assert st != 0 and b"Number of features" in ss.lib().ss_last_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# ranking / metrics
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("rows,cols,L", [(1, 30, 20), (45, 664, 20), (200, 2000, 5), (130, 77, 64)])
+def test_topl_order_bit_exact(ss, o, rows, cols, L):
+    from simspread_b200._lib import check
+    rng = np.random.default_rng(rows + cols + L)
+    R = np.round(rng.random((rows, cols)), 2)  # many ties
+    R[rng.random((rows, cols)) < 0.3] = 0.0
+    R[0, :min(cols, 5)] = [np.nan, -0.0, 0.0, -99.0, np.inf][:min(cols, 5)]
+    ctx = ss.Context.default()
+    d = ss.DMat.from_host(ctx, R)
+    idx, val = ss.DIVec(ctx, L * rows), ss.DMat(ctx, L, rows)
+    check(ss.lib().ss_topl_rows(ctx.h, d.h, L, idx.h, val.h))
+    got = idx.to_host().reshape(rows, L)
+    want = np.stack([o.sortperm_rev(R[r])[:L] for r in range(rows)])
+    assert np.array_equal(got, want)
+    gv = val.to_host().T
+    wv = np.take_along_axis(R, want, axis=1)
+    assert np.array_equal(gv, wv, equal_nan=True)
+
+
+def test_atl_against_oracle(ss, o):
+    rng = np.random.default_rng(11)
+    rows, cols, L = 60, 300, 20
+    R = np.round(rng.random((rows, cols)), 2)
+    Y = (rng.random((rows, cols)) < 0.05).astype(float)
+    y, s = Y.ravel(order="C"), R.ravel(order="C")
+    grp = np.repeat(np.arange(rows), cols)
+    assert ss.recallatL(y, s, grp, L) == pytest.approx(o.recallatL_grouped(y, s, grp, L), rel=1e-12, nan_ok=True)
+    assert ss.precisionatL(y, s, grp, L) == pytest.approx(o.precisionatL_grouped(y, s, grp, L), rel=1e-12)
+    Y[3, :] = 0  # a group without positives: NaN propagates through the mean
+    y = Y.ravel(order="C")
+    assert math.isnan(ss.recallatL(y, s, grp, L)) and math.isnan(o.recallatL_grouped(y, s, grp, L))
+    # ragged groups
+    grp2 = np.concatenate([np.zeros(40), np.ones(100), np.full(rows * cols - 140, 2)])
+    assert ss.precisionatL(y, s, grp2, L) == pytest.approx(o.precisionatL_grouped(y, s, grp2, L), rel=1e-12)
+    assert ss.recallatL(y[:100], s[:100], 7) == pytest.approx(o.recallatL(y[:100], s[:100], 7), rel=1e-12, nan_ok=True)
+
+
+@pytest.mark.parametrize("M,ties", [(2, False), (1000, True), (4096, False), (300000, True), (1 << 20, False)])
+def test_auroc_auprc_against_oracle(ss, o, M, ties):
+    rng = np.random.default_rng(M)
+    y = rng.random(M) < 0.03
+    y[0] = True
+    y[1] = False
+    s = rng.random(M) * (y * 0.3 + 0.7)
+    if ties:
+        s = np.round(s, 3)
+        s[rng.random(M) < 0.5] = 0.0
+    a, p = ss.AuROC(y, s), ss.AuPRC(y, s)
+    assert a == pytest.approx(o.AuROC(y, s), rel=1e-12)
+    assert p == pytest.approx(o.AuPRC(y, s), rel=1e-12)
+
+
+def test_auroc_quirks_and_edges(ss, o):
+    # App. A item 16: no anchors -> not the textbook values
+    assert ss.AuROC([1, 0, 1, 0, 0], [.9, .9, .7, .1, .1]) == pytest.approx(2 / 3, rel=1e-12)
+    assert ss.AuROC([1, 0, 1], [.5, .5, .5]) == 0.0
+    assert ss.AuPRC([1, 0, 1, 0], [.9, .8, .7, .1]) == pytest.approx(0.2916666666666667, rel=1e-12)
+    assert math.isnan(ss.AuROC([0, 0, 0], [.1, .2, .3]))  # no positives: 0/0
+    s = np.array([-99.0, 0.0, 0.5, -99.0, 0.25, 0.0])
+    y = np.array([0, 1, 1, 0, 0, 0])
+    assert ss.AuROC(y, s) == pytest.approx(o.AuROC(y, s), rel=1e-12)
+    with pytest.raises(AssertionError, match="The number of scores must be equal"):
+        ss.AuROC([1, 0], [0.5])
+    assert ss.validity_ratio(s) == o.validity_ratio(s)
+
+
+def test_large_gemm_properties(ss):
+    """Full-width tiles, many k-slabs, multi-wave persistent schedule: integer-valued operands make
+    the result independent of summation order, so it must equal the CPU product exactly."""
+    from simspread_b200._lib import SS_OP_N, check
+    rng = np.random.default_rng(99)
+    M, N, K = 2500, 3000, 2100
+    A = rng.integers(0, 3, size=(M, K)).astype(float)
+    B = rng.integers(-2, 3, size=(K, N)).astype(float)
+    ctx = ss.Context.default()
+    dA, dB, dC = ss.DMat.from_host(ctx, A), ss.DMat.from_host(ctx, B), ss.DMat(ctx, M, N)
+    check(ss.lib().ss_gemm_f64(ctx.h, SS_OP_N, dA.h, dB.h, dC.h, None, None))
+    assert np.array_equal(dC.to_host(), A @ B)
