@@ -120,7 +120,7 @@ __device__ __forceinline__ double finish(double acc, int row, int col, const Gem
 // A_MMAJOR: A is M x K column-major (m contiguous) staged as 8 boxes [16 k][16 m] per slab.
 // !A_MMAJOR: A is stored K x M column-major (k contiguous) staged as one box [128 m][16 k].
 template <bool A_MMAJOR>
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(THREADS, 1)
     ss_dgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
