@@ -289,47 +289,20 @@ def run_b200(args):
     bR, ldr = colmajor(torch, nq_l, nt, dev)
     mR = ss.DMat.wrap(ctx, bR.data_ptr(), nq_l, nt, ldr)
 
+    sharded = None
     if world > 1:
-        bT, ldt = colmajor(torch, nf, nt, dev)       # full transfer matrix, all-gathered
-        bTl, _ = colmajor(torch, nf, nt_l, dev)      # this rank's column block
-        bW, ldw = colmajor(torch, ns, nt_l, dev)
-        assert ldt == bTl.shape[1]
-        mT = ss.DMat.wrap(ctx, bT.data_ptr(), nf, nt, ldt)
-        mTl = ss.DMat.wrap(ctx, bTl.data_ptr(), nf, nt_l, ldt)
-        mW = ss.DMat.wrap(ctx, bW.data_ptr(), ns, nt_l, ldw)
-        tks = torch.zeros(ns, dtype=torch.int32, device=dev)
-        tkf = torch.zeros(nf, dtype=torch.int32, device=dev)
-        tktl = torch.zeros(nt_l, dtype=torch.int32, device=dev)
-        tkt = torch.zeros(nt, dtype=torch.int32, device=dev)
-        def ivec(t_):
-            v = ss.DIVec.__new__(ss.DIVec)
-            v.ctx, v.n = ctx, t_.numel()
-            h = C.c_void_p()
-            check(L.ss_ivec_wrap(ctx.h, C.c_void_p(t_.data_ptr()), t_.numel(), C.byref(h)))
-            v.h = h
-            return v
-        vks, vkf, vktl, vkt = ivec(tks), ivec(tkf), ivec(tktl), ivec(tkt)
+        from simspread_b200.sharded import LibBackend, ShardedPredict, make_plan
+        plan = make_plan(nq, nt, world, rank)
+        sharded = ShardedPredict(plan, LibBackend(ss, ctx, torch, dist, plan, ns, nf, bXq, ldq, bXs, lds, bY, ldy,
+                                                  bR, ldr))
 
     ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     def step():
         if world == 1:
             check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, SS_PREDICT_CLEAN, None))
-            return
-        # degrees: ks = nnz_row(Xs) + sum over ranks of nnz_row(Y block); kf from Xs; kt per block
-        if rank == 0:
-            check(L.ss_degrees(ctx.h, mXs.h, mY.h, vks.h, vkf.h, vktl.h))
         else:
-            check(L.ss_degrees(ctx.h, mXs.h, mY.h, None, vkf.h, vktl.h))
-            check(L.ss_k_rows(ctx.h, mY.h, vks.h))
-        dist.all_reduce(tks)
-        dist.all_gather_into_tensor(tkt, tktl)
-        torch.cuda.current_stream().synchronize()
-        check(L.ss_spread_rows(ctx.h, mY.h, vks.h, mW.h))
-        check(L.ss_gemm_f64(ctx.h, SS_OP_T, mXs.h, mW.h, mTl.h, vkf.h, None))
-        dist.all_gather_into_tensor(bT.view(-1), bTl.view(-1))
-        torch.cuda.current_stream().synchronize()
-        check(L.ss_gemm_f64(ctx.h, SS_OP_N, mXq.h, mT.h, mR.h, None, vkt.h))
+            sharded.step(clean=True)
 
     def barrier():
         ctx.sync()

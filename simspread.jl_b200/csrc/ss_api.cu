@@ -94,6 +94,7 @@ int32_t ss_ctx_destroy(ss_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->ws)
         if (s.p) cudaFree(s.p);
+    if (ctx->tile_counter) cudaFree(ctx->tile_counter);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
@@ -190,9 +191,8 @@ int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
 int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols, int64_t ld, ss_mat** out) {
     SS_ENTER(ctx);
     SS_REQUIRE(out && devptr && rows >= 0 && cols >= 0, "ss_mat_wrap: bad argument");
-    SS_REQUIRE(ld >= rows && (ld % 2) == 0, "ss_mat_wrap: ld (%lld) must be even and >= rows (%lld)",
-               (long long)ld, (long long)rows);
-    SS_REQUIRE((reinterpret_cast<uintptr_t>(devptr) & 15) == 0, "ss_mat_wrap: pointer must be 16-byte aligned");
+    SS_REQUIRE(ld >= rows, "ss_mat_wrap: ld (%lld) must be >= rows (%lld)", (long long)ld, (long long)rows);
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(devptr) & 7) == 0, "ss_mat_wrap: pointer must be 8-byte aligned");
     ss_mat* m = new ss_mat();
     m->ctx = ctx;
     m->d = static_cast<double*>(devptr);

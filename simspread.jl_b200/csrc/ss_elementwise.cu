@@ -118,8 +118,15 @@ __global__ void __launch_bounds__(TPB)
 }
 
 // reference src/core.jl:365-371 : W = G ./ k(G); replace!(W, Inf => 0.0); replace!(W, NaN => 0.0)
-__device__ __forceinline__ double spread1(double x, double kk) {
-    const double q = x / kk;  // IEEE division, as Julia's `/`
+// FP64 division is a ~15-instruction sequence on the (slow) FP64 pipe and would make this pass
+// compute-bound.  Bipartite label / binary feature blocks are almost entirely 0.0 or 1.0, and for
+// those the IEEE quotient is known without dividing: (+-0)/k = +-0 and 1/k = RN(1/k) (computed once
+// per row).  Every other value takes the true division, so the result is bit-identical to `x / k`.
+__device__ __forceinline__ double spread1(double x, double kk, double rk) {
+    double q;
+    if (kk != 0.0 && x == 0.0) q = x;
+    else if (x == 1.0) q = rk;
+    else q = x / kk;  // IEEE division, as Julia's `/`
     return (q != q || q == __longlong_as_double(0x7ff0000000000000ll)) ? 0.0 : q;
 }
 
@@ -131,6 +138,7 @@ __global__ void __launch_bounds__(TPB)
     const bool pair = (r + 1 < rows);
     const double k0 = double(k[r]);
     const double k1 = pair ? double(k[r + 1]) : 1.0;
+    const double r0 = 1.0 / k0, r1 = 1.0 / k1;
     int64_t c = blockIdx.y;
     for (; c + 3 * int64_t(gridDim.y) < cols; c += 4 * int64_t(gridDim.y)) {
         double2 v[4];
@@ -144,8 +152,8 @@ __global__ void __launch_bounds__(TPB)
         for (int u = 0; u < 4; ++u) {
             double* q = W + (c + u * int64_t(gridDim.y)) * ldw + r;
             double2 o;
-            o.x = spread1(v[u].x, k0);
-            o.y = spread1(v[u].y, k1);
+            o.x = spread1(v[u].x, k0, r0);
+            o.y = spread1(v[u].y, k1, r1);
             if (pair) st2(q, o);
             else *q = o.x;
         }
@@ -155,11 +163,11 @@ __global__ void __launch_bounds__(TPB)
         double* q = W + c * ldw + r;
         if (pair) {
             double2 v = ld2(p), o;
-            o.x = spread1(v.x, k0);
-            o.y = spread1(v.y, k1);
+            o.x = spread1(v.x, k0, r0);
+            o.y = spread1(v.y, k1, r1);
             st2(q, o);
         } else {
-            *q = spread1(*p, k0);
+            *q = spread1(*p, k0, r0);
         }
     }
 }
@@ -190,6 +198,8 @@ int32_t launch_featurize(ss_ctx* ctx, const double* S, int64_t rows, int64_t col
                          double alpha, bool weighted, double* X, int64_t ldx) {
     if (rows == 0 || cols == 0) return SS_OK;
     SS_REQUIRE((lds % 2) == 0 && (ldx % 2) == 0, "featurize: leading dimensions must be even");
+    SS_REQUIRE(((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(X)) & 15) == 0,
+               "featurize: matrices must be 16-byte aligned");
     const int64_t gx = ceil_div(ceil_div(rows, 2), TPB);
     dim3 grid(unsigned(gx), pick_grid_y(ctx, gx, cols, 16));
     featurize_kernel<<<grid, TPB, 0, ctx->stream>>>(S, rows, cols, lds, alpha, weighted ? 1 : 0, X, ldx);
@@ -212,7 +222,8 @@ int32_t launch_gather(ss_ctx* ctx, const double* src, int64_t lds, const int32_t
 int32_t launch_degrees(ss_ctx* ctx, const double* M, int64_t rows, int64_t cols, int64_t ld,
                        int32_t* row_deg, int32_t* col_deg) {
     if (rows == 0 || cols == 0) return SS_OK;
-    SS_REQUIRE((ld % 2) == 0, "degrees: leading dimension must be even");
+    SS_REQUIRE((ld % 2) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0,
+               "degrees: matrix must be 16-byte aligned with an even leading dimension");
     const int64_t gx = ceil_div(ceil_div(rows, 2), TPB);
     const int64_t gy = ceil_div(cols, COLS_PER_BLOCK);
     SS_REQUIRE(gy <= 65535, "degrees: too many columns (%lld)", (long long)cols);
@@ -227,6 +238,8 @@ int32_t launch_spread_rows(ss_ctx* ctx, const double* G, int64_t rows, int64_t c
                            const int32_t* k, double* W, int64_t ldw) {
     if (rows == 0 || cols == 0) return SS_OK;
     SS_REQUIRE((ldg % 2) == 0 && (ldw % 2) == 0, "spread: leading dimensions must be even");
+    SS_REQUIRE(((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+               "spread: matrices must be 16-byte aligned");
     const int64_t gx = ceil_div(ceil_div(rows, 2), TPB);
     dim3 grid(unsigned(gx), pick_grid_y(ctx, gx, cols, 16));
     spread_kernel<<<grid, TPB, 0, ctx->stream>>>(G, rows, cols, ldg, k, W, ldw);

@@ -31,6 +31,7 @@ constexpr int A_BYTES = BM * BK * 8;  // 16 KB
 constexpr int B_BYTES = BN * BK * 8;  // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GROUP_M = 16;
+constexpr int SYNC_CHUNK = 64;  // slabs between lockstep checkpoints
 constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -103,6 +104,8 @@ struct GemmParams {
     const int32_t* row_div;   // optional: C[m,:] = acc / row_div[m] (0 when row_div[m] == 0)
     const int32_t* col_flag;  // optional: C[:,n] = -99 when col_flag[n] == 0
     int accumulate;           // C += result
+    int cvec;                 // C (and ldc) allow 16-byte vector stores
+    int* sync_prog;           // optional: per-CTA checkpoint counters for the loose lockstep (see producer)
 };
 
 __device__ __forceinline__ double finish(double acc, int row, int col, const GemmParams& p,
@@ -145,10 +148,31 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int checkpoint = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const TileCoord tc = tile_coord(tile, p.tiles_m, p.tiles_n);
                 const int m0 = tc.tm * BM, n0 = tc.tn * BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
+                    if (p.sync_prog && (kb % SYNC_CHUNK) == 0) {
+                        // Loose lockstep.  The 148 CTAs of a wave share ~25 A/B panels through L2
+                        // only while they stream K at nearby positions; left alone they drift
+                        // apart, every slab is re-fetched from HBM (measured at C4: 10.6 TB
+                        // instead of ~1 TB) and the high fill rate shortens L2 residency further.
+                        // Each producer publishes a checkpoint count every SYNC_CHUNK slabs and
+                        // may run at most one checkpoint ahead of the slowest CTA, so jitter
+                        // averages out instead of adding up as with a hard per-tile barrier.
+                        // The wait is bounded: a CTA that is not co-resident cannot dead-lock us.
+                        ++checkpoint;
+                        *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = checkpoint;
+                        const long long t0 = clock64();
+                        for (;;) {
+                            int mn = 0x7fffffff;
+                            for (int i = 0; i < int(gridDim.x); ++i)
+                                mn = min(mn, *reinterpret_cast<volatile int*>(p.sync_prog + i));
+                            if (mn >= checkpoint - 1 || clock64() - t0 > 400000ll) break;
+                            __nanosleep(256);
+                        }
+                    }
                     const uint32_t full = bar_base + 8 * stage;
                     const uint32_t empty = bar_base + 8 * (STAGES + stage);
                     mbar_wait(empty, phase ^ 1);
@@ -169,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     }
                 }
             }
+            if (p.sync_prog) *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = 0x7fffffff;
         }
         return;
     }
@@ -266,13 +291,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                     for (int b = 0; b < MT / 2; ++b) {
                         const int row = m0 + m_warp + 16 * b + 2 * g;  // rows (row, row+1)
-                        if (row + 1 < p.M) {
+                        if (row + 1 < p.M && p.cvec) {
                             double2 v;
                             v.x = finish(acc[2 * b][j][e], row, col, p, ccol + row);
                             v.y = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
                             *reinterpret_cast<double2*>(ccol + row) = v;
-                        } else if (row < p.M) {
-                            ccol[row] = finish(acc[2 * b][j][e], row, col, p, ccol + row);
+                        } else {
+                            if (row < p.M) ccol[row] = finish(acc[2 * b][j][e], row, col, p, ccol + row);
+                            if (row + 1 < p.M)
+                                ccol[row + 1] = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
                         }
                     }
                 } else {
@@ -337,11 +364,10 @@ int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, cons
     SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem (M=%lld N=%lld K=%lld)", (long long)M,
                (long long)N, (long long)K);
     SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
-    SS_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0 && (ldc % 2) == 0,
-               "gemm: leading dimensions must be even (16-byte TMA / vector alignment)");
-    SS_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
-               "gemm: operands must be 16-byte aligned");
+    SS_REQUIRE((lda % 2) == 0 && (ldb % 2) == 0, "gemm: lda / ldb must be even (16-byte TMA alignment)");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "gemm: A and B must be 16-byte aligned");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(C) & 7) == 0, "gemm: C must be 8-byte aligned");
     CUtensorMap mapA, mapB;
     if (opA == SS_OP_N) {
         SS_TRY(make_map(&mapA, A, M, K, lda, 16, 16));
@@ -360,9 +386,16 @@ int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, cons
     p.row_div = row_div;
     p.col_flag = col_flag;
     p.accumulate = accumulate ? 1 : 0;
+    p.cvec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 2) == 0) ? 1 : 0;
+    p.sync_prog = nullptr;
     const int64_t total = int64_t(p.tiles_m) * p.tiles_n;
     SS_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
     const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);
+    if (total > grid) {  // more than one wave: keep the waves in lockstep for L2 reuse
+        if (!ctx->tile_counter) SS_CHECK_CUDA(cudaMalloc(&ctx->tile_counter, 4096));
+        SS_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, size_t(grid) * 4, ctx->stream));
+        p.sync_prog = ctx->tile_counter;
+    }
     if (!ctx->gemm_attr_set) {
         SS_CHECK_CUDA(cudaFuncSetAttribute(ss_dgemm_kernel<true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));

@@ -616,3 +616,113 @@ def recall(tn, fp, fn, tp):
 def precision(tn, fp, fn, tp):
     _chk(tn, fp, fn, tp)
     return float("nan") if tp + fp == 0 else tp / (tp + fp)
+
+
+# ------------------------------------------------------------------------------------------------
+# Drivers for the loops the reference leaves to user code (docs/src/api.md:17-21):
+# k-fold de-novo cross-validation and the alpha sweep.  Everything stays on the GPU between the
+# upload of (DD, DT) and the download of the predictions / metrics.
+# ------------------------------------------------------------------------------------------------
+
+
+def _names_only(rows, cols) -> NamedArray:
+    """A NamedArray that carries names but no values (index bookkeeping for device-resident data)."""
+    n = NamedArray.__new__(NamedArray)
+    n.array = np.empty((len(rows), 0), dtype=np.bool_)
+    n._names = [[str(r) for r in rows], [str(c) for c in cols]]
+    return n
+
+
+def _fold_indices(X: NamedArray, y: NamedArray, queries: Sequence[str]):
+    """Index lists of construct(y, X, queries) (reference src/core.jl:152-154)."""
+    qset = set(queries)
+    xr, xc = X.names(1), X.names(2)
+    features = [f for f in xc if f.lstrip("f") not in qset]
+    sources = [d for d in xr if d not in qset]
+    _assert_names_differ(features, sources, "Source and Features nodes have the same names!")
+    return (X.index_of(queries, 1), X.index_of(sources, 1), X.index_of(features, 2), y.index_of(sources, 1),
+            y.index_of(queries, 1))
+
+
+def cross_validate(DT: NamedArray, DD: NamedArray, alpha: float, weighted: bool = True, k_: int = 10,
+                   seed: int = 1, L: int = 20, folds: Optional[List[List[str]]] = None) -> dict:
+    """k-fold de-novo cross-validation: `split` -> `featurize` -> per fold `construct`, `predict`,
+    `clean!` -> AuROC / AuPRC over all (query, target) pairs and mean recall@L / precision@L per
+    query.  Returns the predictions with rows in fold order."""
+    ctx = Context.default()
+    assert DT.size(1) == DD.size(1), "Labels and features have different number of source nodes"
+    if folds is None:
+        folds = split(DT, k_, seed=seed)
+    order = [q for f in folds for q in f]
+    N, nt = DT.size(1), DT.size(2)
+    dX = DMat.from_host(ctx, DD.array)
+    check(lib().ss_featurize(ctx.h, dX.h, float(alpha), int(bool(weighted)), dX.h))  # featurize! on device
+    Xn = _names_only(DD.names(1), ["f" + c for c in DD.names(2)])  # the values live on the GPU
+    dy = DMat.from_host(ctx, DT.array)
+    Rall = DMat(ctx, len(order), nt)
+    _, _, ldR, pR = Rall.info()
+    off = 0
+    for queries in folds:
+        if not queries:
+            continue
+        qi, si, fi, ysi, _ = _fold_indices(Xn, DT, queries)
+        Xq, Xs = DMat(ctx, len(qi), len(fi)), DMat(ctx, len(si), len(fi))
+        Y = DMat(ctx, len(si), nt)
+        dqi, dsi, dfi, dysi = (DIVec.from_host(ctx, a) for a in (qi, si, fi, ysi))
+        check(lib().ss_gather(ctx.h, dX.h, dqi.h, dfi.h, Xq.h))
+        check(lib().ss_gather(ctx.h, dX.h, dsi.h, dfi.h, Xs.h))
+        check(lib().ss_gather(ctx.h, dy.h, dysi.h, None, Y.h))
+        Rv = DMat.wrap(ctx, pR + 8 * off, len(qi), nt, ldR)  # rows [off, off+nq) of Rall
+        if len(si) and len(fi):
+            check(lib().ss_predict_query(ctx.h, Xq.h, Xs.h, Y.h, Rv.h, SS_PREDICT_CLEAN, None))
+        off += len(qi)
+    perm = DIVec.from_host(ctx, DT.index_of(order, 1))
+    Yall = DMat(ctx, len(order), nt)
+    check(lib().ss_gather(ctx.h, dy.h, perm.h, None, Yall.h))
+    auc = (C.c_double * 2)()
+    check(lib().ss_auroc_auprc_mat(ctx.h, Yall.h, Rall.h, auc))
+    res = {"folds": folds, "AuROC": float(auc[0]), "AuPRC": float(auc[1])}
+    if nt > L:
+        atl = (C.c_double * 2)()
+        check(lib().ss_atl(ctx.h, Yall.h, Rall.h, int(L), atl))
+        res["recallatL"], res["precisionatL"] = float(atl[0]), float(atl[1])
+    res["yhat"] = NamedArray(Rall.to_host(), (order, DT.names(2)))
+    res["y"] = NamedArray(Yall.to_host(), (order, DT.names(2)))
+    return res
+
+
+def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: Sequence[float],
+                weighted: bool = True, L: int = 20, rank: int = 0, world: int = 1) -> List[dict]:
+    """SimSpread's alpha sweep (BASELINE config 3): for every cutoff alpha, featurize -> construct
+    -> predict -> clean! -> metrics on the same query set.  alpha points are independent, so with
+    `world` > 1 rank r evaluates alphas[r::world] (no communication)."""
+    ctx = Context.default()
+    queries = [str(q) for q in queries]
+    dS = DMat.from_host(ctx, DD.array)
+    dX = DMat(ctx, DD.size(1), DD.size(2))
+    dy = DMat.from_host(ctx, DT.array)
+    Xn = _names_only(DD.names(1), ["f" + c for c in DD.names(2)])
+    qi, si, fi, ysi, yqi = _fold_indices(Xn, DT, queries)
+    nt = DT.size(2)
+    dqi, dsi, dfi, dysi, dyqi = (DIVec.from_host(ctx, a) for a in (qi, si, fi, ysi, yqi))
+    Xq, Xs = DMat(ctx, len(qi), len(fi)), DMat(ctx, len(si), len(fi))
+    Y, Yq, R = DMat(ctx, len(si), nt), DMat(ctx, len(qi), nt), DMat(ctx, len(qi), nt)
+    check(lib().ss_gather(ctx.h, dy.h, dysi.h, None, Y.h))
+    check(lib().ss_gather(ctx.h, dy.h, dyqi.h, None, Yq.h))
+    kq = DIVec(ctx, len(qi))
+    out = []
+    for a in list(alphas)[rank::world]:
+        check(lib().ss_featurize(ctx.h, dS.h, float(a), int(bool(weighted)), dX.h))
+        check(lib().ss_gather(ctx.h, dX.h, dqi.h, dfi.h, Xq.h))
+        check(lib().ss_gather(ctx.h, dX.h, dsi.h, dfi.h, Xs.h))
+        check(lib().ss_predict_query(ctx.h, Xq.h, Xs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
+        auc, atl = (C.c_double * 2)(), (C.c_double * 2)()
+        check(lib().ss_auroc_auprc_mat(ctx.h, Yq.h, R.h, auc))
+        rec = {"alpha": float(a), "AuROC": float(auc[0]), "AuPRC": float(auc[1])}
+        if nt > L:
+            check(lib().ss_atl(ctx.h, Yq.h, R.h, int(L), atl))
+            rec["recallatL"], rec["precisionatL"] = float(atl[0]), float(atl[1])
+        check(lib().ss_k_rows(ctx.h, R.h, kq.h))
+        rec["validity_ratio"] = float(kq.to_host().astype(np.int64).sum() / (len(qi) * nt))
+        out.append(rec)
+    return out

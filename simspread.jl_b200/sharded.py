@@ -1,0 +1,161 @@
+"""Multi-GPU form of predict for query rows (one process per GPU).
+
+Sharding of R = Xq * T,  T = (Xs' * (Y ./ ks)) ./ kf:
+  * rank r owns the query-row slab Xq[r] / R[r]              -> no communication;
+  * T is built cooperatively by target-column block: rank r holds Y[:, r], computes
+    Wst[:, r] = Y[:, r] ./ ks and T[:, r] = (Xs' * Wst[:, r]) ./ kf with the replicated Xs; column
+    blocks of the column-major T are contiguous, so ONE all-gather assembles T on every rank;
+  * degrees: kf from the replicated Xs; ks = nnz_row(Xs) + sum_r nnz_row(Y[:, r]) -> all-reduce of
+    an int32 vector (rank 0 contributes the Xs term); kt[r] = nnz_col(Y[:, r]) -> all-gather
+    (needed only by the fused clean!).
+
+`ShardedPredict.step()` is the choreography; the numerical work is delegated to a backend.  The
+product backend (`LibBackend`) calls libsimspread_b200 on device buffers owned by torch and uses
+torch.distributed (NCCL) for the three collectives.  tests/test_sharded_gloo.py drives the same
+choreography at world_size 2 on CPU with a NumPy test double and the gloo backend."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    nq: int
+    nt: int
+    nq_blk: int  # rows per rank (ceil); the last ranks may own fewer (or zero) real rows
+    nt_blk: int  # target columns per rank (ceil)
+
+    @property
+    def q0(self) -> int:
+        return min(self.nq, self.rank * self.nq_blk)
+
+    @property
+    def nq_local(self) -> int:
+        return max(0, min(self.nq_blk, self.nq - self.rank * self.nq_blk))
+
+    @property
+    def t0(self) -> int:
+        return min(self.nt, self.rank * self.nt_blk)
+
+    @property
+    def nt_local(self) -> int:
+        return max(0, min(self.nt_blk, self.nt - self.rank * self.nt_blk))
+
+    @property
+    def nt_padded(self) -> int:
+        return self.nt_blk * self.world
+
+
+def make_plan(nq: int, nt: int, world: int, rank: int) -> ShardPlan:
+    assert world >= 1 and 0 <= rank < world
+    return ShardPlan(world, rank, nq, nt, -(-nq // world), -(-nt // world))
+
+
+class ShardedPredict:
+    """Choreography of one sharded spread+predict step.  `backend` provides:
+         degrees(with_xs_rows: bool)   fill ks_part (nnz_row(Y blk) [+ nnz_row(Xs)]), kf, kt_blk
+         all_reduce_ks(), all_gather_kt(), all_gather_T()
+         spread()                      Wst blk = Y blk ./ ks
+         gemm_T()                      T blk = (Xs' * Wst blk) ./ kf
+         gemm_R(clean: bool)           R slab = Xq slab * T   (+ clean! flag from kt)
+    """
+
+    def __init__(self, plan: ShardPlan, backend):
+        self.plan, self.b = plan, backend
+
+    def step(self, clean: bool = True):
+        b = self.b
+        b.degrees(with_xs_rows=(self.plan.rank == 0))
+        if self.plan.world > 1:
+            b.all_reduce_ks()
+            b.all_gather_kt()
+        b.spread()
+        b.gemm_T()
+        if self.plan.world > 1:
+            b.all_gather_T()
+        b.gemm_R(clean)
+
+
+class LibBackend:
+    """Product backend: libsimspread_b200 kernels on torch-owned device buffers + NCCL."""
+
+    def __init__(self, ss, ctx, torch, dist, plan: ShardPlan, ns: int, nf: int, bXq, ldq, bXs, lds, bY, ldy, bR, ldr):
+        from ._lib import check
+        self.ss, self.ctx, self.torch, self.dist, self.plan, self.check = ss, ctx, torch, dist, plan, check
+        self.L = ss.lib()
+        dev = bXs.device
+        p = plan
+        self.ns, self.nf = ns, nf
+        ld16 = lambda n: (n + 15) // 16 * 16
+        self.mXq = ss.DMat.wrap(ctx, bXq.data_ptr(), p.nq_local, nf, ldq)
+        self.mXs = ss.DMat.wrap(ctx, bXs.data_ptr(), ns, nf, lds)
+        self.mY = ss.DMat.wrap(ctx, bY.data_ptr(), ns, p.nt_blk, ldy)
+        self.mR = ss.DMat.wrap(ctx, bR.data_ptr(), p.nq_local, p.nt, ldr)
+        self.ldt = ld16(nf)
+        self.bW = torch.zeros((p.nt_blk, ld16(ns)), dtype=torch.float64, device=dev)
+        self.mW = ss.DMat.wrap(ctx, self.bW.data_ptr(), ns, p.nt_blk, ld16(ns))
+        self.tks = torch.zeros(ns, dtype=torch.int32, device=dev)
+        self.tkf = torch.zeros(nf, dtype=torch.int32, device=dev)
+        self.tkt = torch.zeros(p.nt_padded, dtype=torch.int32, device=dev)
+        self.tktl = torch.zeros(p.nt_blk, dtype=torch.int32, device=dev)
+        self.bT = torch.zeros((p.nt_padded, self.ldt), dtype=torch.float64, device=dev)
+        if p.world > 1:
+            self.bTl = torch.zeros((p.nt_blk, self.ldt), dtype=torch.float64, device=dev)
+        else:
+            self.bTl = self.bT
+        self.mT = ss.DMat.wrap(ctx, self.bT.data_ptr(), nf, p.nt, self.ldt)
+        self.mTl = ss.DMat.wrap(ctx, self.bTl.data_ptr(), nf, p.nt_blk, self.ldt)
+        self.vks, self.vkf = self._ivec(self.tks), self._ivec(self.tkf)
+        self.vktl = self._ivec(self.tktl)
+        self.vkt = self._ivec(self.tkt[:p.nt])
+
+    def _ivec(self, t):
+        v = self.ss.DIVec.__new__(self.ss.DIVec)
+        v.ctx, v.n = self.ctx, t.numel()
+        h = C.c_void_p()
+        self.check(self.L.ss_ivec_wrap(self.ctx.h, C.c_void_p(t.data_ptr()), t.numel(), C.byref(h)))
+        v.h = h
+        return v
+
+    def _wait_collective(self):
+        self.torch.cuda.current_stream().synchronize()
+
+    def degrees(self, with_xs_rows: bool):
+        L, c = self.L, self.ctx.h
+        if with_xs_rows:
+            self.check(L.ss_degrees(c, self.mXs.h, self.mY.h, self.vks.h, self.vkf.h, self.vktl.h))
+        else:
+            self.check(L.ss_degrees(c, self.mXs.h, self.mY.h, None, self.vkf.h, self.vktl.h))
+            self.check(L.ss_k_rows(c, self.mY.h, self.vks.h))
+        if self.plan.world == 1:
+            self.tkt[:self.plan.nt_blk].copy_(self.tktl)
+            self._wait_collective()
+
+    def all_reduce_ks(self):
+        self.dist.all_reduce(self.tks)
+        self._wait_collective()
+
+    def all_gather_kt(self):
+        self.dist.all_gather_into_tensor(self.tkt, self.tktl)
+        self._wait_collective()
+
+    def spread(self):
+        self.check(self.L.ss_spread_rows(self.ctx.h, self.mY.h, self.vks.h, self.mW.h))
+
+    def gemm_T(self):
+        from ._lib import SS_OP_T
+        self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h, None))
+
+    def all_gather_T(self):
+        self.dist.all_gather_into_tensor(self.bT.view(-1), self.bTl.view(-1))
+        self._wait_collective()
+
+    def gemm_R(self, clean: bool):
+        from ._lib import SS_OP_N
+        if self.plan.nq_local == 0:
+            return
+        self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_N, self.mXq.h, self.mT.h, self.mR.h, None,
+                                      self.vkt.h if clean else None))

@@ -429,3 +429,98 @@ def test_large_gemm_properties(ss):
     dA, dB, dC = ss.DMat.from_host(ctx, A), ss.DMat.from_host(ctx, B), ss.DMat(ctx, M, N)
     check(ss.lib().ss_gemm_f64(ctx.h, SS_OP_N, dA.h, dB.h, dC.h, None, None))
     assert np.array_equal(dC.to_host(), A @ B)
+
+
+def test_sharded_backend_world1_matches_single_call(ss, o):
+    """The N > 1 product backend (LibBackend) on one GPU must reproduce ss_predict_query exactly."""
+    import torch
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    from simspread_b200.sharded import LibBackend, ShardedPredict, make_plan
+    nq, ns, nf, nt = 200, 150, 130, 90
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=9, y_density=0.05, alpha=0.2, weighted=True)
+    Y[:, 3] = 0.0
+    ctx = ss.Context.default()
+    dev = torch.device("cuda", ctx.device)
+
+    def put(a):
+        ld = (a.shape[0] + 15) // 16 * 16
+        buf = torch.zeros((a.shape[1], ld), dtype=torch.float64, device=dev)
+        buf[:, :a.shape[0]] = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
+        return buf, ld
+
+    (bXq, ldq), (bXs, lds), (bY, ldy) = put(Xq), put(Xs), put(Y)
+    bR, ldr = put(np.zeros((nq, nt)))
+    torch.cuda.synchronize()
+    plan = make_plan(nq, nt, 1, 0)
+    be = LibBackend(ss, ctx, torch, None, plan, ns, nf, bXq, ldq, bXs, lds, bY, ldy, bR, ldr)
+    ShardedPredict(plan, be).step(clean=True)
+    got = bR[:, :nq].T.cpu().numpy()
+    dq, dx, dy, R = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y, np.zeros((nq, nt))))
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+    assert np.array_equal(got, R.to_host())
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    assert relerr(got, want) < RTOL
+
+
+def test_cross_validate_enzyme_shape_against_oracle_loop(ss, o):
+    """BASELINE config 2: Enzyme-shaped (445 x 664), binary alpha-cutoff features, 10-fold CV."""
+    S, Yfull = _enzyme_like(o, seed=20242)
+    N, Nt = Yfull.shape
+    names = [f"D{i:04d}" for i in range(N)]
+    tnames = [f"T{j:04d}" for j in range(Nt)]
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Yfull, (names, tnames))
+    res = ss.cross_validate(DT, DD, 0.35, weighted=False, k_=10, seed=1, L=20)
+    folds = res["folds"]
+    assert len(folds) == 10 and sorted(sum(folds, [])) == sorted(names)
+    Xo, xr, xc = o.featurize(S, names, names, 0.35, False)
+    want, order = [], []
+    for q in folds:
+        Ao, Bo, nn = o.construct_queries(Yfull, (names, tnames), Xo, (xr, xc), q)
+        w = o.predict_dense(Ao, Bo, nn, q, tnames)
+        o.clean(w, Ao, nn, tnames)
+        want.append(w)
+        order += q
+    want = np.vstack(want)
+    assert res["yhat"].names(1) == order
+    assert relerr(res["yhat"].array, want) < RTOL
+    assert np.array_equal(res["yhat"].array == -99, want == -99)
+    ytrue = Yfull[[names.index(x) for x in order]]
+    assert np.array_equal(res["y"].array, ytrue)
+    # metrics on the reference-path scores (ties resolve identically only for identical scores)
+    assert res["AuROC"] == pytest.approx(o.AuROC(ytrue.ravel() > 0, res["yhat"].array.ravel()), rel=1e-12)
+    assert res["AuPRC"] == pytest.approx(o.AuPRC(ytrue.ravel() > 0, res["yhat"].array.ravel()), rel=1e-12)
+    grp = np.repeat(np.arange(N), Nt)
+    sc = res["yhat"].array.ravel()
+    assert res["precisionatL"] == pytest.approx(o.precisionatL_grouped(ytrue.ravel(), sc, grp, 20), rel=1e-12)
+    r = o.recallatL_grouped(ytrue.ravel(), sc, grp, 20)
+    assert (math.isnan(r) and math.isnan(res["recallatL"])) or res["recallatL"] == pytest.approx(r, rel=1e-12)
+
+
+def test_alpha_sweep_against_oracle(ss, o):
+    """BASELINE config 3 (scaled): weighted SimSpread over alpha in 0..1, dense end to empty end."""
+    rng = np.random.default_rng(33)
+    nq, ns, nt = 120, 260, 150
+    N = nq + ns
+    names = [f"n{i}" for i in range(N)]
+    tn = [f"t{j}" for j in range(nt)]
+    S = np.round(rng.random((N, N)), 6)
+    Yl = (rng.random((N, nt)) < 0.02).astype(float)
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Yl, (names, tn))
+    queries = names[:nq]
+    alphas = [0.0, 0.25, 0.5, 0.9, 1.0]
+    got = ss.alpha_sweep(DT, DD, queries, alphas, weighted=True, L=20)
+    both = ss.alpha_sweep(DT, DD, queries, alphas, weighted=True, L=20, rank=1, world=2)
+    assert [g["alpha"] for g in both] == alphas[1::2]
+    for g in got:
+        Xo, xr, xc = o.featurize(S, names, names, g["alpha"], True)
+        Ao, Bo, nn = o.construct_queries(Yl, (names, tn), Xo, (xr, xc), queries)
+        w = o.predict_dense(Ao, Bo, nn, queries, tn)
+        o.clean(w, Ao, nn, tn)
+        yq = Yl[:nq]
+        # score ties at exactly-equal sums can differ in the last bit between the two summation
+        # orders, so the metric is compared on the oracle's own scores with a small tolerance
+        assert g["AuROC"] == pytest.approx(o.AuROC(yq.ravel() > 0, w.ravel()), rel=1e-9, nan_ok=True)
+        assert g["AuPRC"] == pytest.approx(o.AuPRC(yq.ravel() > 0, w.ravel()), rel=1e-9, nan_ok=True)
+        assert g["validity_ratio"] == o.validity_ratio(w)
+    assert got[-1]["validity_ratio"] <= got[0]["validity_ratio"]

@@ -1,0 +1,119 @@
+"""Per-kernel throughput of the HBM-bound passes of the path ("also report featurize
+(elements/s, GB/s) and metric kernels (scores/s) individually").  CUDA events on the library
+stream, best and median of 10 after 3 warm-ups; inputs are far larger than the 126 MB L2.
+Writes gpurun_out/kernels.json; run under gpurun on one B200."""
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simspread_b200 as ss
+from simspread_b200._lib import check
+
+HBM = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+ctx = ss.Context(0)
+L = ss.lib()
+dev = torch.device("cuda:0")
+ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+
+def colmajor(rows, cols, fill):
+    ld = (rows + 15) // 16 * 16
+    buf = torch.empty((cols, ld), dtype=torch.float64, device=dev)
+    step = max(1, (1 << 27) // ld)
+    for c0 in range(0, cols, step):
+        fill(buf[c0:c0 + step])
+    torch.cuda.synchronize()
+    return buf, ss.DMat.wrap(ctx, buf.data_ptr(), rows, cols, ld)
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        fn()
+        e1.record(ext)
+        ctx.sync()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), statistics.median(ts)
+
+
+out = {"hbm_peak_gbs": HBM, "kernels": []}
+
+
+def report(name, units, unit_name, bytes_alg, fn, note=""):
+    best, med = timed(fn)
+    rec = {"kernel": name, "units": units, "unit": unit_name, "ms_best": best, "ms_median": med,
+           "units_per_s": units / (med * 1e-3), "algorithmic_bytes": bytes_alg,
+           "achieved_gbs": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_alg / (med * 1e-3) / 1e9 / HBM,
+           "note": note}
+    out["kernels"].append(rec)
+    print(json.dumps(rec), flush=True)
+
+
+uni = lambda b: b.copy_(torch.round(torch.rand(b.shape, device=dev, dtype=torch.float64) * 1e6) / 1e6)
+bern = lambda b: b.copy_((torch.rand(b.shape, device=dev) < 0.05).to(torch.float64))
+
+# featurize: C4-sized similarity block (100000 x 20000 = 16 GB), weighted, alpha 0.5, out of place
+rows, cols = 100_000, 20_000
+bS, mS = colmajor(rows, cols, uni)
+bX, mX = colmajor(rows, cols, lambda b: b.zero_())
+n = rows * cols
+report("featurize_kernel (dense, weighted, alpha=0.5)", n, "elements", 16 * n,
+       lambda: check(L.ss_featurize(ctx.h, mS.h, 0.5, 1, mX.h)), "8 B read + 8 B write per element")
+
+
+def csr(alpha, weighted):
+    h = C.c_void_p()
+    check(L.ss_featurize_csr(ctx.h, mS.h, alpha, weighted, C.byref(h)))
+    nnz = C.c_int64()
+    check(L.ss_csr_info(h, None, None, C.byref(nnz), None))
+    L.ss_csr_destroy(h)
+    return nnz.value
+
+
+nnz = csr(0.9, 1)
+report("featurize_csr (count + scan + fill, weighted, alpha=0.9)", n, "elements", 16 * n + 12 * nnz + 4 * rows,
+       lambda: csr(0.9, 1), f"2 x 8 B read per element + 12 B per kept edge ({nnz} edges); includes cudaMalloc of the CSR")
+del bX, mX
+
+# degrees + spread on C4's Xs / Y
+bXs, mXs = colmajor(20_000, 20_000, uni)
+bY, mY = colmajor(20_000, 50_000, bern)
+bW, mW = colmajor(20_000, 50_000, lambda b: b.zero_())
+ks, kf, kt = ss.DIVec(ctx, 20_000), ss.DIVec(ctx, 20_000), ss.DIVec(ctx, 50_000)
+n2 = 20_000 * 20_000 + 20_000 * 50_000
+report("degrees_kernel x2 (ks, kf, kt of C4)", n2, "elements", 8 * n2 + 4 * 90_000,
+       lambda: check(L.ss_degrees(ctx.h, mXs.h, mY.h, ks.h, kf.h, kt.h)), "8 B read per element")
+n3 = 20_000 * 50_000
+report("spread_kernel (Wst = Y ./ ks)", n3, "elements", 16 * n3,
+       lambda: check(L.ss_spread_rows(ctx.h, mY.h, ks.h, mW.h)), "8 B read + 8 B write per element")
+del bS, mS, bW, mW
+
+# top-L and recall/precision@L on a C4-sized score matrix (100000 x 50000 = 40 GB)
+bR, mR = colmajor(100_000, 50_000, uni)
+idx = ss.DIVec(ctx, 20 * 100_000)
+nr = 100_000 * 50_000
+report("topl_kernel (L = 20)", nr, "scores", 8 * nr,
+       lambda: check(L.ss_topl_rows(ctx.h, mR.h, 20, idx.h, None)), "8 B read per score")
+del bR, mR
+
+# AuROC / AuPRC on 10^8 (label, score) pairs (6-digit scores -> many ties)
+M = 100_000_000
+sc = torch.round(torch.rand(M, device=dev, dtype=torch.float64) * 1e6) / 1e6
+lb = (torch.rand(M, device=dev) < 0.01).to(torch.uint8)
+torch.cuda.synchronize()
+res = (C.c_double * 2)()
+report("auroc_auprc (radix sort + curve scan), M = 1e8", M, "scores", 9 * M * (2 + 3 * 8),
+       lambda: check(L.ss_auroc_auprc(ctx.h, C.c_void_p(lb.data_ptr()), C.c_void_p(sc.data_ptr()), M, res)),
+       "9 B per score x (key build + histogram + <= 8 passes x (upsweep read, downsweep read + write))")
+out["auroc_auprc_value"] = [res[0], res[1]]
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/kernels.json", "w"), indent=1)
