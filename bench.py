@@ -383,6 +383,35 @@ def run_b200(args):
         rel = ((got - want).abs() / want.abs().clamp_min(1e-300)).max().item()
         checkres = {"sampled_entries": 64, "max_rel_err": rel, "tolerance": 1e-12, "ok": bool(rel < 1e-12)}
 
+    if not args.no_check and world > 1:
+        # (i) every rank must hold the same all-gathered T; (ii) entries of this rank's R slab whose
+        # target column lies in this rank's Y block are recomputed with torch/cuBLAS + torch collectives
+        be = sharded.b
+        cs = be.bT.sum().reshape(1)
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        same_T = all(bool(torch.equal(allcs[0], c)) for c in allcs)
+        g = torch.Generator(device="cpu")
+        g.manual_seed(11 + rank)
+        tq = torch.randint(0, nq_l, (32,), generator=g).to(dev)
+        tl = torch.randint(0, nt_l, (32,), generator=g).to(dev)
+        Xs_v, Y_v = bXs[:, :ns], bY[:, :ns]
+        ky = (Y_v != 0).sum(0).to(torch.int64)
+        dist.all_reduce(ky)
+        ks_ = (Xs_v != 0).sum(0) + ky
+        kf_ = (Xs_v != 0).sum(1)
+        kt_ = (Y_v != 0).sum(1)
+        Wst_cols = torch.nan_to_num(Y_v[tl] / ks_.to(torch.float64), nan=0.0, posinf=0.0)
+        Tcols = Xs_v @ Wst_cols.T
+        Tcols = torch.where(kf_[:, None] > 0, Tcols / kf_[:, None].to(torch.float64), torch.zeros_like(Tcols))
+        want = (bXq[:, :nq_l].T[tq] * Tcols.T).sum(1)
+        want = torch.where(kt_[tl] == 0, torch.full_like(want, -99.0), want)
+        got = bR[tl + t0, tq]
+        rel = ((got - want).abs() / want.abs().clamp_min(1e-300)).max().reshape(1)
+        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+        checkres = {"sampled_entries": 32 * world, "max_rel_err": float(rel.item()), "tolerance": 1e-12,
+                    "ok": bool(rel.item() < 1e-12 and same_T), "all_ranks_hold_identical_T": same_T}
+
     # ---- e2e: reference-facing host-buffer call, H2D/D2H inside the timed region ----------------------
     e2e = None
     if not args.no_e2e:

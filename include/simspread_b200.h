@@ -110,6 +110,9 @@ SS_API int32_t ss_featurize(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t 
  * warp-ballot kernel; values are stored when weighted != 0.  An entry is kept iff the
  * thresholded value is an edge for src/graphs.jl:10 (non-zero). */
 SS_API int32_t ss_featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out);
+/* Same, but the CSR of S' (one CSR row per COLUMN of S, ascending row index) -- the natural
+ * direction for a column-major S and the form the sparse chain needs for Xs (features x sources). */
+SS_API int32_t ss_featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out);
 SS_API int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values);
 SS_API int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t* col_idx, double* values);
 SS_API int32_t ss_csr_destroy(ss_csr* c);
@@ -143,6 +146,11 @@ SS_API int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_m
  * context stream.  kt_out (optional) receives the target degrees used by clean!. */
 SS_API int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
                          uint32_t flags, ss_ivec* kt_out);
+/* Sparse form of ss_predict_query for high-alpha (few-percent dense) feature blocks: Xq is the CSR
+ * of the Nq x Nf query block, XsT the CSR of Xs' (Nf x Ns, from ss_featurize_csc), Y the dense
+ * Ns x Nt label block.  Both products run as row-split SpMMs; R is dense column-major as before. */
+SS_API int32_t ss_predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr* XsT, const ss_mat* Y, ss_mat* R,
+                                    uint32_t flags, ss_ivec* kt_out);
 /* predict(A, ytrain) / source rows [src/core.jl:446-466]: R = Xs*T + Y*U, U = (Y' ./ kt)*(Y ./ ks).
  * Xs may be NULL (classical 2-layer NBI: R = Y*U). */
 SS_API int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ss_ivec_download": (c_i32, [vp, vp, vp]),
     "ss_featurize": (c_i32, [vp, vp, c_f64, c_i32, vp]),
     "ss_featurize_csr": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),
+    "ss_featurize_csc": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),
     "ss_csr_info": (c_i32, [vp, P(c_i64), P(c_i64), P(c_i64), P(c_i32)]),
     "ss_csr_download": (c_i32, [vp, vp, vp, vp, vp]),
     "ss_csr_destroy": (c_i32, [vp]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "ss_spread_rows": (c_i32, [vp, vp, vp, vp]),
     "ss_gemm_f64": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp]),
     "ss_predict_query": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
+    "ss_predict_query_csr": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
     "ss_predict_source": (c_i32, [vp, vp, vp, vp, c_u32]),
     "ss_clean": (c_i32, [vp, vp, vp]),
     "ss_predict_query_host": (c_i32, [vp, vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i64, c_i64,

@@ -354,6 +354,14 @@ int32_t ss_featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t wei
     return SS_OK;
 }
 
+int32_t ss_featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(S && out, "ss_featurize_csc: null argument");
+    SS_TRY(featurize_csc(ctx, S, alpha, weighted != 0, out));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
 int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values) {
     SS_REQUIRE(c, "ss_csr_info: null csr");
     if (rows) *rows = c->rows;
@@ -521,6 +529,19 @@ int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const 
                            nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, false));
     if (kt_out)
         SS_CHECK_CUDA(cudaMemcpyAsync(kt_out->d, w.kt, size_t(Y->cols) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr* XsT, const ss_mat* Y, ss_mat* R,
+                             uint32_t flags, ss_ivec* kt_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Xq && XsT && Y && R, "ss_predict_query_csr: null argument");
+    SS_REQUIRE(Xq->cols == XsT->rows, "Number of features between test and training sets doesn't match");
+    SS_REQUIRE(XsT->cols == Y->rows, "Labels and features have different number of source nodes");
+    SS_REQUIRE(R->rows == Xq->rows && R->cols == Y->cols, "ss_predict_query_csr: R must be Nq x Nt");
+    SS_REQUIRE(!kt_out || kt_out->n == Y->cols, "ss_predict_query_csr: kt_out has wrong length");
+    SS_TRY(predict_query_csr(ctx, Xq, XsT, Y, R, flags, kt_out ? kt_out->d : nullptr));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }

@@ -158,6 +158,51 @@ class DIVec:
             pass
 
 
+class DCsr:
+    """Device CSR handle (`ss_csr`)."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        r, c, n, v = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        check(lib().ss_csr_info(h, C.byref(r), C.byref(c), C.byref(n), C.byref(v)))
+        self.rows, self.cols, self.nnz, self.has_values = r.value, c.value, n.value, bool(v.value)
+
+    @classmethod
+    def from_dense(cls, ctx: Context, S: "DMat", alpha: float, weighted: bool, by_columns: bool = False) -> "DCsr":
+        """Threshold + compact (`ss_featurize_csr`), or the CSR of S' with by_columns=True
+        (`ss_featurize_csc`)."""
+        h = C.c_void_p()
+        fn = lib().ss_featurize_csc if by_columns else lib().ss_featurize_csr
+        check(fn(ctx.h, S.h, float(alpha), int(bool(weighted)), C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def density(self) -> float:
+        return self.nnz / max(1, self.rows * self.cols)
+
+    def to_host(self):
+        rp = np.empty(self.rows + 1, np.int32)
+        ci = np.empty(max(self.nnz, 1), np.int32)
+        va = np.empty(max(self.nnz, 1), np.float64)
+        check(lib().ss_csr_download(self.ctx.h, self.h, rp.ctypes.data, ci.ctypes.data,
+                                    va.ctypes.data if self.has_values else None))
+        return rp, ci[:self.nnz], (va[:self.nnz] if self.has_values else None)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().ss_csr_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+# Below this density of both feature blocks the row-split SpMM chain beats the DMMA chain: one
+# partial product costs 8 B of L2/HBM traffic (~1.2e-12 s at 6.5 TB/s) against 2 flop of a dense
+# FP64 GEMM (~5.5e-14 s at 36 TFLOP/s) -> break-even near 4.5 % (DESIGN.md 4.2).
+SPARSE_DENSITY_THRESHOLD = 0.04
+
+
 def _h(x):
     return x.h if x is not None else None
 
@@ -272,6 +317,15 @@ class Graph:
         self.features, self.targets = list(features), list(targets)
         self.Xq, self.Xs, self.Y = Xq, Xs, Y
         self.masked = masked
+        self._csr = None
+
+    def csr(self):
+        """(CSR of Xq, CSR of Xs') of the already-featurized blocks, built on first use."""
+        if self._csr is None:
+            ninf = float("-inf")  # keep every stored non-zero of the featurized block
+            self._csr = (DCsr.from_dense(self.ctx, self.Xq, ninf, True),
+                         DCsr.from_dense(self.ctx, self.Xs, ninf, True, by_columns=True))
+        return self._csr
 
     def names(self, d: Optional[int] = None):
         n = [str(x) for x in self.queries + self.sources + self.features + self.targets]
@@ -399,13 +453,16 @@ def _dense_predict(A: NamedArray, B: NamedArray, rows, cols) -> NamedArray:
     return Fn[list(rows), list(cols)]
 
 
-def predict(*args, GPU: bool = False, clean: bool = False) -> NamedArray:
+def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto") -> NamedArray:
     """`predict((A, B), ytest)`, `predict(A, B, ytest)` (reference src/core.jl:402-425) and
     `predict(A, ytrain)` (:446-466).  Returns `F[names(ytest,1), names(ytest,2)]`.
 
     `GPU` is accepted for signature compatibility: this implementation always runs on the GPU, in
     Float64 (the reference's GPU=true silently drops to Float32, src/core.jl:404).  `clean=True`
-    (extension) fuses `clean!` into the product's epilogue."""
+    (extension) fuses `clean!` into the product's epilogue.  `layout` (extension) selects the dense
+    DMMA chain, the sparse row-split SpMM chain, or picks by the density of the feature blocks."""
+    if layout not in ("auto", "dense", "sparse"):
+        raise ValueError("layout must be 'auto', 'dense' or 'sparse'")
     ctx = Context.default()
     if len(args) == 2 and isinstance(args[0], tuple):
         (A, B), yq = args
@@ -441,7 +498,16 @@ def predict(*args, GPU: bool = False, clean: bool = False) -> NamedArray:
             return _dense_predict(A.to_named(), A.to_named(), rows, cols)
         R = DMat(ctx, len(g.queries), nt)
         if len(g.features) and len(g.sources):
-            check(lib().ss_predict_query(ctx.h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, None))
+            use_sparse = layout == "sparse"
+            if layout == "auto":
+                cq, cs = g.csr()
+                use_sparse = max(cq.density, cs.density) < SPARSE_DENSITY_THRESHOLD
+            if use_sparse:
+                cq, cs = g.csr()
+                check(lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, g.Y.h, R.h, flags, None))
+            else:
+                check(lib().ss_predict_query(ctx.h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, None))
+            g.last_layout = "sparse" if use_sparse else "dense"
         Rh = R.to_host()
         for i, qi in want_q:
             out[i, :] = Rh[qi, ci]

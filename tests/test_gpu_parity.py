@@ -524,3 +524,75 @@ def test_alpha_sweep_against_oracle(ss, o):
         assert g["AuPRC"] == pytest.approx(o.AuPRC(yq.ravel() > 0, w.ravel()), rel=1e-9, nan_ok=True)
         assert g["validity_ratio"] == o.validity_ratio(w)
     assert got[-1]["validity_ratio"] <= got[0]["validity_ratio"]
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (300, 7), (445, 445), (1000, 333)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_featurize_csc_bit_exact(ss, o, rows, cols, weighted):
+    rng = np.random.default_rng(rows + 17 * cols)
+    S = np.round(rng.random((rows, cols)), 3)
+    S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = np.nan
+    S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = 0.0
+    ctx = ss.Context.default()
+    d = ss.DMat.from_host(ctx, S)
+    for alpha in (0.35, 0.0, 0.95, 1.01):
+        want = o.cutoff(S, alpha, weighted)
+        c = ss.DCsr.from_dense(ctx, d, alpha, weighted, by_columns=True)
+        rp, ci, va = c.to_host()
+        wc, wr = np.nonzero(want.T != 0)  # CSR of S': row = column of S, ascending row index
+        assert (c.rows, c.cols, c.nnz) == (cols, rows, len(wr))
+        assert np.array_equal(rp, np.concatenate(([0], np.cumsum(np.bincount(wc, minlength=cols)))).astype(np.int32))
+        assert np.array_equal(ci, wr.astype(np.int32))
+        if weighted:
+            assert np.array_equal(va, want[wr, wc])
+        else:
+            assert va is None
+
+
+@pytest.mark.parametrize("weighted,alpha", [(True, 0.9), (False, 0.97), (True, 0.5), (True, 1.01)])
+def test_predict_sparse_chain_against_oracle_and_dense(ss, o, weighted, alpha):
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    nq, ns, nf, nt = 333, 410, 410, 517
+    rng = np.random.default_rng(int(alpha * 100))
+    Xq = o.cutoff(np.round(rng.random((nq, nf)), 6), alpha, weighted)
+    Xs = o.cutoff(np.round(rng.random((ns, nf)), 6), alpha, weighted)
+    Y = (rng.random((ns, nt)) < 0.03).astype(float)
+    Y[:, 5] = 0.0
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    ctx = ss.Context.default()
+    dq, dx, dy = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y))
+    cq = ss.DCsr.from_dense(ctx, dq, float("-inf"), True)
+    cs = ss.DCsr.from_dense(ctx, dx, float("-inf"), True, by_columns=True)
+    assert cq.nnz == np.count_nonzero(Xq) and cs.nnz == np.count_nonzero(Xs)
+    R = ss.DMat.from_host(ctx, np.full((nq, nt), 3.0))
+    kt = ss.DIVec(ctx, nt)
+    check(ss.lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, dy.h, R.h, SS_PREDICT_CLEAN, kt.h))
+    got = R.to_host()
+    assert relerr(got, want) < RTOL and np.array_equal(got == -99, want == -99)
+    assert np.array_equal(kt.to_host(), o.degrees_blocks(Xs, Y)[2])
+    Rd = ss.DMat(ctx, nq, nt)
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, Rd.h, SS_PREDICT_CLEAN, None))
+    assert relerr(Rd.to_host(), want) < RTOL
+
+
+def test_predict_layout_auto_switch(ss, o):
+    rng = np.random.default_rng(4)
+    N, nt = 400, 90
+    names = [f"n{i}" for i in range(N)]
+    tn = [f"t{j}" for j in range(nt)]
+    S = np.round(rng.random((N, N)), 6)
+    Yl = (rng.random((N, nt)) < 0.05).astype(float)
+    DT = ss.NamedArray(Yl, (names, tn))
+    q = names[:80]
+    for alpha, expect in ((0.3, "dense"), (0.985, "sparse")):
+        X = ss.featurize(ss.NamedArray(S, (names, names)), alpha, True)
+        A, B = ss.construct(DT, X, q)
+        auto = ss.predict((A, B), DT[q, tn])
+        assert A.last_layout == expect
+        dense = ss.predict((A, B), DT[q, tn], layout="dense")
+        sparse = ss.predict((A, B), DT[q, tn], layout="sparse")
+        Ao, Bo, nn = o.construct_queries(Yl, (names, tn), X.array, (names, X.names(2)), q)
+        want = o.predict_dense(Ao, Bo, nn, q, tn)
+        for got in (auto, dense, sparse):
+            assert relerr(got.array, want) < RTOL
