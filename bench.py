@@ -416,7 +416,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq, bXs, bY, ldq, lds, ldy,
-                      step if world > 1 else None,
+                      sharded,
                       (mXq, mXs, mY, mR, bR, ldr))
 
     if rank == 0:
@@ -431,7 +431,9 @@ def run_b200(args):
                        "nq": nq, "ns": ns, "nf": nf, "nt": nt, "y_density": d["y_density"], "alpha": d["alpha"],
                        "weighted": d["weighted"], "clean_fused": True,
                        "sharding": "single GPU" if world == 1 else
-                       f"query rows x{world}; T by target-column block + NCCL all-gather",
+                       (f"query rows x{world}; T by target-column block, " +
+                        ("blocks stored to all peers from the T-GEMM epilogue over NVLink P2P (fused all-gather)"
+                         if sharded.b.mirrors is not None else "NCCL all-gather")),
                        "l2": "inputs (27 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "check": checkres,
@@ -493,12 +495,13 @@ def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq
             check(L.ss_predict_query_host(ctx.h, pXq, nq_e, pXs, ns, pY, ns, nq_e, ns, nf, nt, SS_PREDICT_CLEAN,
                                           pR, nq_e))
     else:
+        be = sharded_step.b
+
         def e2e_step():
-            check(L.ss_mat_upload(ctx.h, mXq.h, pXq, nq_e))
             check(L.ss_mat_upload(ctx.h, mXs.h, pXs, ns))
             check(L.ss_mat_upload(ctx.h, mY.h, pY, ns))
-            sharded_step()
-            check(L.ss_mat_download(ctx.h, mR.h, pR, nq_e))
+            sharded_step.front()  # degrees, spread, T block, fused all-gather of T
+            check(L.ss_stream_product_host(ctx.h, pXq, nq_e, nq_e, be.mT.h, be.vkt.h, pR, nq_e))
 
     e2e_step()  # warm-up (allocates the streaming workspaces)
     ctx.sync()
@@ -525,7 +528,7 @@ def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq
         "d2h_bytes_per_step": int(nq_e * nt * 8 * world),
         "ms_per_step": wall * 1e3, "steps": nsteps, "queries": nq_e * world,
         "api": "ss_predict_query_host (pinned host buffers, slab-pipelined H2D / GEMM / D2H)" if world == 1 else
-               "ss_mat_upload + sharded step + ss_mat_download per rank",
+               "per rank: ss_mat_upload(Xs, Y block) + sharded front (T over NVLink) + ss_stream_product_host",
         "matches_resident_run": same,
     }
     for p in (pXq, pXs, pY, pR):

@@ -140,6 +140,18 @@ SS_API int32_t ss_spread_rows(ss_ctx* ctx, const ss_mat* G, const ss_ivec* k, ss
  * B is K x N column-major. */
 SS_API int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
                     const ss_ivec* row_div, const ss_ivec* col_flag);
+/* Fused GEMM + all-gather for the multi-GPU chain: as ss_gemm_f64, and every element of C is also
+ * stored, from the epilogue, to `n_mirrors` (<= 7) peer-GPU matrices with the same leading dimension
+ * (`mirrors[i]` = device address, mapped into this process, of the peer's element C(0,0)) over
+ * NVLink P2P.  The caller synchronises the ranks afterwards (stream sync + barrier). */
+SS_API int32_t ss_gemm_f64_mirrored(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
+                                    const ss_ivec* row_div, const ss_ivec* col_flag, int32_t n_mirrors,
+                                    void* const* mirrors);
+/* CUDA IPC plumbing for the mirrors: 64-byte handle of a library-owned matrix, and mapping of a
+ * peer's handle into this process (peer access is enabled lazily). */
+SS_API int32_t ss_mat_ipc_handle(ss_ctx* ctx, const ss_mat* m, void* handle64_out);
+SS_API int32_t ss_ipc_open(ss_ctx* ctx, const void* handle64, void** devptr_out);
+SS_API int32_t ss_ipc_close(ss_ctx* ctx, void* devptr);
 /* predict((A,B), ytest) for query rows [src/core.jl:402-423 with the blocks of :165-198]:
  *   R = Xq * T,  T = (Xs' ./ kf) * (Y ./ ks)      
  * Xq: Nq x Nf, Xs: Ns x Nf, Y: Ns x Nt, R: Nq x Nt.  Runs degrees -> spread -> T -> R on the
@@ -163,6 +175,12 @@ SS_API int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt);
 SS_API int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const double* Xs, int64_t ldxs,
                               const double* Y, int64_t ldy, int64_t nq, int64_t ns, int64_t nf, int64_t nt,
                               uint32_t flags, double* R, int64_t ldr);
+
+/* Second half of the same call for callers that already hold T on the device (multi-GPU: T comes
+ * from the sharded chain): R_host (nq x N) = Xq_host (nq x K) * T (K x N) with the clean! flag of
+ * col_flag (optional), query-row slabs streamed H2D / GEMM / D2H on three streams. */
+SS_API int32_t ss_stream_product_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, int64_t nq, const ss_mat* T,
+                                      const ss_ivec* col_flag, double* R, int64_t ldr);
 
 /* ---- (4) ranking + metrics ----------------------------------------------------------------- */
 /* Per-row top-L of R under `sortperm(row; rev=true)` order [src/performance.jl:315,377]:

@@ -64,12 +64,17 @@ SIGNATURES = {
     "ss_k_rows": (c_i32, [vp, vp, vp]),
     "ss_spread_rows": (c_i32, [vp, vp, vp, vp]),
     "ss_gemm_f64": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp]),
+    "ss_gemm_f64_mirrored": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp, c_i32, P(vp)]),
+    "ss_mat_ipc_handle": (c_i32, [vp, vp, vp]),
+    "ss_ipc_open": (c_i32, [vp, vp, P(vp)]),
+    "ss_ipc_close": (c_i32, [vp, vp]),
     "ss_predict_query": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
     "ss_predict_query_csr": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
     "ss_predict_source": (c_i32, [vp, vp, vp, vp, c_u32]),
     "ss_clean": (c_i32, [vp, vp, vp]),
     "ss_predict_query_host": (c_i32, [vp, vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i64, c_i64,
                                       c_u32, vp, c_i64]),
+    "ss_stream_product_host": (c_i32, [vp, vp, c_i64, c_i64, vp, vp, vp, c_i64]),
     "ss_topl_rows": (c_i32, [vp, vp, c_i32, vp, vp]),
     "ss_atl": (c_i32, [vp, vp, vp, c_i32, P(c_f64)]),
     "ss_auroc_auprc": (c_i32, [vp, vp, vp, c_i64, P(c_f64)]),

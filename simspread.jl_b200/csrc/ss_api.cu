@@ -84,6 +84,14 @@ int32_t ss_ctx_create(int32_t device, ss_ctx** out) {
     SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     SS_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    {   // keep freed CSR buffers in the default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return SS_OK;
 }
@@ -387,9 +395,10 @@ int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t*
 int32_t ss_csr_destroy(ss_csr* c) {
     if (!c) return SS_OK;
     cudaSetDevice(c->ctx->device);
-    if (c->row_ptr) cudaFree(c->row_ptr);
-    if (c->col_idx) cudaFree(c->col_idx);
-    if (c->values) cudaFree(c->values);
+    // stream-ordered pool allocations (cudaMallocAsync): no device-wide synchronisation per CSR
+    if (c->row_ptr) cudaFreeAsync(c->row_ptr, c->ctx->stream);
+    if (c->col_idx) cudaFreeAsync(c->col_idx, c->ctx->stream);
+    if (c->values) cudaFreeAsync(c->values, c->ctx->stream);
     delete c;
     return SS_OK;
 }
@@ -472,6 +481,54 @@ int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, 
     SS_TRY(launch_gemm_f64(ctx, opA, A->d, A->ld, B->d, B->ld, C->d, C->ld, M, B->cols, K,
                            row_div ? row_div->d : nullptr, col_flag ? col_flag->d : nullptr, false));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_gemm_f64_mirrored(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
+                             const ss_ivec* row_div, const ss_ivec* col_flag, int32_t n_mirrors, void* const* mirrors) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(A && B && C, "ss_gemm_f64_mirrored: null matrix");
+    SS_REQUIRE(opA == SS_OP_N || opA == SS_OP_T, "ss_gemm_f64_mirrored: bad opA");
+    SS_REQUIRE(n_mirrors >= 0 && n_mirrors <= 7 && (n_mirrors == 0 || mirrors), "ss_gemm_f64_mirrored: 0..7 mirrors");
+    const int64_t M = (opA == SS_OP_N) ? A->rows : A->cols;
+    const int64_t K = (opA == SS_OP_N) ? A->cols : A->rows;
+    SS_REQUIRE(B->rows == K && C->rows == M && C->cols == B->cols, "ss_gemm_f64_mirrored: shape mismatch");
+    SS_REQUIRE(!row_div || row_div->n == M, "ss_gemm_f64_mirrored: row_div has wrong length");
+    SS_REQUIRE(!col_flag || col_flag->n == B->cols, "ss_gemm_f64_mirrored: col_flag has wrong length");
+    double* mp[7] = {nullptr};
+    for (int i = 0; i < n_mirrors; ++i) {
+        SS_REQUIRE(mirrors[i] && (reinterpret_cast<uintptr_t>(mirrors[i]) & 7) == 0, "ss_gemm_f64_mirrored: bad mirror pointer");
+        mp[i] = static_cast<double*>(mirrors[i]);
+    }
+    SS_TRY(launch_gemm_f64(ctx, opA, A->d, A->ld, B->d, B->ld, C->d, C->ld, M, B->cols, K,
+                           row_div ? row_div->d : nullptr, col_flag ? col_flag->d : nullptr, false, n_mirrors, mp));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_mat_ipc_handle(ss_ctx* ctx, const ss_mat* m, void* handle64_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && handle64_out, "ss_mat_ipc_handle: null argument");
+    SS_REQUIRE(m->owned, "ss_mat_ipc_handle: only library-owned matrices (ss_mat_create) can be shared");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SS_CHECK_CUDA(cudaIpcGetMemHandle(&h, m->d));
+    memcpy(handle64_out, &h, 64);
+    return SS_OK;
+}
+
+int32_t ss_ipc_open(ss_ctx* ctx, const void* handle64, void** devptr_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(handle64 && devptr_out, "ss_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SS_CHECK_CUDA(cudaIpcOpenMemHandle(devptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SS_OK;
+}
+
+int32_t ss_ipc_close(ss_ctx* ctx, void* devptr) {
+    SS_ENTER(ctx);
+    if (devptr) SS_CHECK_CUDA(cudaIpcCloseMemHandle(devptr));
     return SS_OK;
 }
 
@@ -582,35 +639,12 @@ int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt) {
     return SS_OK;
 }
 
-// Host-buffer form: Xs / Y are uploaded once, then query-row slabs of Xq stream in on copy_in while
-// the R GEMM of the previous slab runs on `stream` and finished R slabs stream out on copy_out.
-int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const double* Xs, int64_t ldxs,
-                              const double* Y, int64_t ldy, int64_t nq, int64_t ns, int64_t nf, int64_t nt,
-                              uint32_t flags, double* R, int64_t ldr) {
-    SS_ENTER(ctx);
-    SS_REQUIRE(nq >= 0 && ns >= 0 && nf >= 0 && nt >= 0, "ss_predict_query_host: negative dimension");
-    SS_REQUIRE(ldxq >= nq && ldxs >= ns && ldy >= ns && ldr >= nq, "ss_predict_query_host: leading dimension too small");
-    if (nq == 0 || nt == 0) return SS_OK;
-    SS_REQUIRE(Xq && Xs && Y && R, "ss_predict_query_host: null buffer");
-    if (ns == 0 || nf == 0) {
-        for (int64_t c = 0; c < nt; ++c) memset(R + c * ldr, 0, size_t(nq) * 8);
-        return SS_OK;
-    }
-    // resident operands
-    ss_mat mXs, mY;
+// R_host (nq x nt) = Xq_host (nq x nf) * T (device, nf x nt) [+ clean! flag], streamed: query-row slabs
+// of Xq go up on copy_in while the GEMM of the previous slab runs on `stream` and finished R slabs
+// come down on copy_out (double-buffered; overlap needs pinned host memory).
+static int32_t stream_product(ss_ctx* ctx, const double* Xq, int64_t ldxq, int64_t nq, int64_t nf, const double* T,
+                              int64_t ldt, int64_t nt, const int32_t* col_flag, double* R, int64_t ldr) {
     void* p;
-    mXs.ctx = mY.ctx = ctx;
-    mXs.rows = ns; mXs.cols = nf; mXs.ld = round_up(ns, 16);
-    mY.rows = ns; mY.cols = nt; mY.ld = round_up(ns, 16);
-    SS_TRY(scratch_get(ctx, 4, size_t(mXs.ld) * size_t(nf) * 8, &p));
-    mXs.d = static_cast<double*>(p);
-    SS_TRY(scratch_get(ctx, 5, size_t(mY.ld) * size_t(nt) * 8, &p));
-    mY.d = static_cast<double*>(p);
-    SS_TRY(copy2d(ctx, ctx->stream, mXs.d, mXs.ld, Xs, ldxs, ns, nf, cudaMemcpyHostToDevice));
-    SS_TRY(copy2d(ctx, ctx->stream, mY.d, mY.ld, Y, ldy, ns, nt, cudaMemcpyHostToDevice));
-    ChainWs w;
-    SS_TRY(chain_front(ctx, &mXs, &mY, &w));
-
     // slab size: about 1 GiB of Xq+R per buffer, multiple of 128 rows
     int64_t slab = (int64_t(1) << 30) / ((nf + nt) * 8);
     slab = slab / 128 * 128;
@@ -648,8 +682,8 @@ int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const
         // GEMM slab i (needs its input and the download that last read this R buffer)
         cudaStreamWaitEvent(ctx->stream, in_done[b], 0);
         if (i >= 2) cudaStreamWaitEvent(ctx->stream, out_done[b], 0);
-        status = launch_gemm_f64(ctx, SS_OP_N, dXq[b], slab, w.T, w.ldt, dR[b], slab, nr, nt, nf, nullptr,
-                                 (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, false);
+        status = launch_gemm_f64(ctx, SS_OP_N, dXq[b], slab, T, ldt, dR[b], slab, nr, nt, nf, nullptr,
+                                 col_flag, false);
         if (status != SS_OK) break;
         cudaEventRecord(mm_done[b], ctx->stream);
         // download slab i
@@ -670,6 +704,52 @@ int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const
     SS_CHECK_CUDA(e2);
     SS_CHECK_CUDA(e3);
     return SS_OK;
+}
+
+// Host-buffer form: Xs / Y are uploaded once, then query-row slabs of Xq stream in on copy_in while
+// the R GEMM of the previous slab runs on `stream` and finished R slabs stream out on copy_out.
+int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, const double* Xs, int64_t ldxs,
+                              const double* Y, int64_t ldy, int64_t nq, int64_t ns, int64_t nf, int64_t nt,
+                              uint32_t flags, double* R, int64_t ldr) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(nq >= 0 && ns >= 0 && nf >= 0 && nt >= 0, "ss_predict_query_host: negative dimension");
+    SS_REQUIRE(ldxq >= nq && ldxs >= ns && ldy >= ns && ldr >= nq, "ss_predict_query_host: leading dimension too small");
+    if (nq == 0 || nt == 0) return SS_OK;
+    SS_REQUIRE(Xq && Xs && Y && R, "ss_predict_query_host: null buffer");
+    if (ns == 0 || nf == 0) {
+        for (int64_t c = 0; c < nt; ++c) memset(R + c * ldr, 0, size_t(nq) * 8);
+        return SS_OK;
+    }
+    // resident operands
+    ss_mat mXs, mY;
+    void* p;
+    mXs.ctx = mY.ctx = ctx;
+    mXs.rows = ns; mXs.cols = nf; mXs.ld = round_up(ns, 16);
+    mY.rows = ns; mY.cols = nt; mY.ld = round_up(ns, 16);
+    SS_TRY(scratch_get(ctx, 4, size_t(mXs.ld) * size_t(nf) * 8, &p));
+    mXs.d = static_cast<double*>(p);
+    SS_TRY(scratch_get(ctx, 5, size_t(mY.ld) * size_t(nt) * 8, &p));
+    mY.d = static_cast<double*>(p);
+    SS_TRY(copy2d(ctx, ctx->stream, mXs.d, mXs.ld, Xs, ldxs, ns, nf, cudaMemcpyHostToDevice));
+    SS_TRY(copy2d(ctx, ctx->stream, mY.d, mY.ld, Y, ldy, ns, nt, cudaMemcpyHostToDevice));
+    ChainWs w;
+    SS_TRY(chain_front(ctx, &mXs, &mY, &w));
+
+    return stream_product(ctx, Xq, ldxq, nq, nf, w.T, w.ldt, nt, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, R, ldr);
+}
+
+int32_t ss_stream_product_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, int64_t nq, const ss_mat* T,
+                               const ss_ivec* col_flag, double* R, int64_t ldr) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(T && nq >= 0 && ldxq >= nq && ldr >= nq, "ss_stream_product_host: bad argument");
+    SS_REQUIRE(!col_flag || col_flag->n == T->cols, "ss_stream_product_host: col_flag has wrong length");
+    if (nq == 0 || T->cols == 0) return SS_OK;
+    SS_REQUIRE(Xq && R, "ss_stream_product_host: null buffer");
+    if (T->rows == 0) {
+        for (int64_t c = 0; c < T->cols; ++c) memset(R + c * ldr, 0, size_t(nq) * 8);
+        return SS_OK;
+    }
+    return stream_product(ctx, Xq, ldxq, nq, T->rows, T->d, T->ld, T->cols, col_flag ? col_flag->d : nullptr, R, ldr);
 }
 
 // ---- (4) ranking / metrics ---------------------------------------------------------------------

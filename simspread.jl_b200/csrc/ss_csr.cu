@@ -121,7 +121,7 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
         ss_csr_destroy(c);
         return s;
     };
-    if (cudaMalloc(&c->row_ptr, size_t(rows + 2) * 4) != cudaSuccess) {
+    if (cudaMallocAsync(reinterpret_cast<void**>(&c->row_ptr), size_t(rows + 2) * 4, ctx->stream) != cudaSuccess) {
         cudaGetLastError();
         set_error("featurize_csr: out of device memory");
         return fail(SS_ERR_OOM);
@@ -154,7 +154,8 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
     }
     c->nnz = h[0];
     const size_t n1 = size_t(c->nnz > 0 ? c->nnz : 1);
-    if (cudaMalloc(&c->col_idx, n1 * 4) != cudaSuccess || (weighted && cudaMalloc(&c->values, n1 * 8) != cudaSuccess)) {
+    if (cudaMallocAsync(reinterpret_cast<void**>(&c->col_idx), n1 * 4, ctx->stream) != cudaSuccess ||
+        (weighted && cudaMallocAsync(reinterpret_cast<void**>(&c->values), n1 * 8, ctx->stream) != cudaSuccess)) {
         cudaGetLastError();
         set_error("featurize_csr: out of device memory for %lld edges", (long long)c->nnz);
         return fail(SS_ERR_OOM);

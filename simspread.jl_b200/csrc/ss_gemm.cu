@@ -106,7 +106,18 @@ struct GemmParams {
     int accumulate;           // C += result
     int cvec;                 // C (and ldc) allow 16-byte vector stores
     int* sync_prog;           // optional: per-CTA checkpoint counters for the loose lockstep (see producer)
+    int nmirror;              // fused all-gather: every C element is also stored to these peer-GPU
+    double* mirror[7];        // copies of C (same ld), over NVLink P2P, straight from the epilogue
 };
+
+__device__ __forceinline__ void store1(const GemmParams& p, int64_t off, double v) {
+    p.C[off] = v;
+    for (int i = 0; i < p.nmirror; ++i) p.mirror[i][off] = v;
+}
+__device__ __forceinline__ void store2(const GemmParams& p, int64_t off, double2 v) {
+    *reinterpret_cast<double2*>(p.C + off) = v;
+    for (int i = 0; i < p.nmirror; ++i) *reinterpret_cast<double2*>(p.mirror[i] + off) = v;
+}
 
 __device__ __forceinline__ double finish(double acc, int row, int col, const GemmParams& p,
                                          const double* cptr) {
@@ -286,7 +297,8 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int e = 0; e < 2; ++e) {
                 const int col = n0 + n_warp + 8 * j + t + 4 * e;  // rho(2t+e) = t + 4e
                 if (col >= p.N) continue;
-                double* ccol = p.C + int64_t(col) * p.ldc;
+                const int64_t coff = int64_t(col) * p.ldc;
+                const double* ccol = p.C + coff;
                 if (A_MMAJOR) {
 #pragma unroll
                     for (int b = 0; b < MT / 2; ++b) {
@@ -295,18 +307,19 @@ __global__ void __launch_bounds__(THREADS, 1)
                             double2 v;
                             v.x = finish(acc[2 * b][j][e], row, col, p, ccol + row);
                             v.y = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
-                            *reinterpret_cast<double2*>(ccol + row) = v;
+                            store2(p, coff + row, v);
                         } else {
-                            if (row < p.M) ccol[row] = finish(acc[2 * b][j][e], row, col, p, ccol + row);
+                            if (row < p.M) store1(p, coff + row, finish(acc[2 * b][j][e], row, col, p, ccol + row));
                             if (row + 1 < p.M)
-                                ccol[row + 1] = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
+                                store1(p, coff + row + 1,
+                                       finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1));
                         }
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
                         const int row = m0 + m_warp + 8 * i + rg;
-                        if (row < p.M) ccol[row] = finish(acc[i][j][e], row, col, p, ccol + row);
+                        if (row < p.M) store1(p, coff + row, finish(acc[i][j][e], row, col, p, ccol + row));
                     }
                 }
             }
@@ -360,7 +373,8 @@ namespace ss {
 
 int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                        const int32_t* row_div, const int32_t* col_flag, bool accumulate) {
+                        const int32_t* row_div, const int32_t* col_flag, bool accumulate, int nmirror,
+                        double* const* mirrors) {
     SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem (M=%lld N=%lld K=%lld)", (long long)M,
                (long long)N, (long long)K);
     SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
@@ -388,6 +402,11 @@ int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, cons
     p.accumulate = accumulate ? 1 : 0;
     p.cvec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 2) == 0) ? 1 : 0;
     p.sync_prog = nullptr;
+    SS_REQUIRE(nmirror >= 0 && nmirror <= 7 && !(nmirror && accumulate), "gemm: bad mirror request");
+    p.nmirror = nmirror;
+    for (int i = 0; i < 7; ++i) p.mirror[i] = (i < nmirror) ? mirrors[i] : nullptr;
+    for (int i = 0; i < nmirror; ++i)
+        if (reinterpret_cast<uintptr_t>(mirrors[i]) & 15) p.cvec = 0;
     const int64_t total = int64_t(p.tiles_m) * p.tiles_n;
     SS_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
     const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);

@@ -67,6 +67,11 @@ class ShardedPredict:
         self.plan, self.b = plan, backend
 
     def step(self, clean: bool = True):
+        self.front()
+        self.b.gemm_R(clean)
+
+    def front(self):
+        """Everything up to the assembled T (and kt) on every rank."""
         b = self.b
         b.degrees(with_xs_rows=(self.plan.rank == 0))
         if self.plan.world > 1:
@@ -76,7 +81,14 @@ class ShardedPredict:
         b.gemm_T()
         if self.plan.world > 1:
             b.all_gather_T()
-        b.gemm_R(clean)
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ carrier: a torch view of library-owned device memory."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
 
 
 class LibBackend:
@@ -101,16 +113,51 @@ class LibBackend:
         self.tkf = torch.zeros(nf, dtype=torch.int32, device=dev)
         self.tkt = torch.zeros(p.nt_padded, dtype=torch.int32, device=dev)
         self.tktl = torch.zeros(p.nt_blk, dtype=torch.int32, device=dev)
-        self.bT = torch.zeros((p.nt_padded, self.ldt), dtype=torch.float64, device=dev)
-        if p.world > 1:
-            self.bTl = torch.zeros((p.nt_blk, self.ldt), dtype=torch.float64, device=dev)
-        else:
-            self.bTl = self.bT
-        self.mT = ss.DMat.wrap(ctx, self.bT.data_ptr(), nf, p.nt, self.ldt)
-        self.mTl = ss.DMat.wrap(ctx, self.bTl.data_ptr(), nf, p.nt_blk, self.ldt)
+        # T is library-owned (plain cudaMalloc) so that its IPC handle can be mapped by the peers;
+        # bT is a torch view of the same memory (checks, NCCL fallback).
+        self.mTfull = ss.DMat(ctx, nf, p.nt_padded)
+        _, _, ldt_, pT = self.mTfull.info()
+        assert ldt_ == self.ldt
+        self.bT = torch.as_tensor(_CudaView(pT, (p.nt_padded, self.ldt)), device=dev)
+        self.mT = ss.DMat.wrap(ctx, pT, nf, p.nt, self.ldt)
+        blk_off = p.rank * p.nt_blk * self.ldt * 8           # my column block inside any rank's T
+        self.mTl = ss.DMat.wrap(ctx, pT + blk_off, nf, p.nt_blk, self.ldt)
+        self.bTl = self.bT[p.rank * p.nt_blk:(p.rank + 1) * p.nt_blk]
+        self.mirrors = None
+        import os
+        if p.world > 1 and os.environ.get("SS_FUSED_ALLGATHER", "1") != "0":
+            self._open_peers(pT, blk_off)
         self.vks, self.vkf = self._ivec(self.tks), self._ivec(self.tkf)
         self.vktl = self._ivec(self.tktl)
         self.vkt = self._ivec(self.tkt[:p.nt])
+
+    def _open_peers(self, pT, blk_off):
+        """Exchange CUDA IPC handles of T and map every peer's T: the T-GEMM epilogue then stores this
+        rank's column block straight into all peers (fused GEMM + all-gather over NVLink)."""
+        torch, dist, L = self.torch, self.dist, self.L
+        hbuf = (C.c_ubyte * 64)()
+        self.check(L.ss_mat_ipc_handle(self.ctx.h, self.mTfull.h, hbuf))
+        mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.bT.device)
+        allh = torch.zeros(64 * self.plan.world, dtype=torch.uint8, device=self.bT.device)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().reshape(self.plan.world, 64)
+        ptrs = []
+        try:
+            for r in range(self.plan.world):
+                if r == self.plan.rank:
+                    continue
+                raw = (C.c_ubyte * 64)(*allh[r].tolist())
+                dp = C.c_void_p()
+                self.check(L.ss_ipc_open(self.ctx.h, raw, C.byref(dp)))
+                ptrs.append(dp.value)
+        except Exception as e:  # no P2P / IPC on this box: keep the NCCL all-gather
+            print(f"[simspread_b200] rank {self.plan.rank}: peer mapping failed ({e}); using NCCL all-gather")
+            ptrs = None
+        ok = torch.tensor([1 if ptrs is not None else 0], device=self.bT.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            self.peer_bases = ptrs
+            self.mirrors = (C.c_void_p * len(ptrs))(*[p_ + blk_off for p_ in ptrs])
 
     def _ivec(self, t):
         v = self.ss.DIVec.__new__(self.ss.DIVec)
@@ -147,10 +194,19 @@ class LibBackend:
 
     def gemm_T(self):
         from ._lib import SS_OP_T
-        self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h, None))
+        if self.mirrors is not None:
+            self.check(self.L.ss_gemm_f64_mirrored(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h,
+                                                   None, len(self.mirrors), self.mirrors))
+        else:
+            self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h, None))
 
     def all_gather_T(self):
-        self.dist.all_gather_into_tensor(self.bT.view(-1), self.bTl.view(-1))
+        if self.mirrors is not None:
+            # every rank's epilogue has already written its block into every T (the GEMM call
+            # returns after its stream has drained); a barrier orders those writes before the R GEMM
+            self.dist.barrier()
+        else:
+            self.dist.all_gather_into_tensor(self.bT.view(-1), self.bTl.reshape(-1).clone())
         self._wait_collective()
 
     def gemm_R(self, clean: bool):
