@@ -51,6 +51,14 @@ extern "C" {
 /* ss_predict_* flags */
 #define SS_PREDICT_CLEAN 1u /* fuse clean! (src/core.jl:478-484): columns with kt == 0 -> -99 */
 
+/* precision of the two chain products, OR-ed into the ss_predict_* flags (default FP64 on the DMMA
+ * pipe).  SS_PRECISION_TF32 is the opt-in fast mode, the analogue of the reference's reduced
+ * precision GPU=true path (Float32 cuBLAS SGEMM, src/core.jl:404): operands rounded to TF32,
+ * tcgen05.mma kind::tf32, FP32 accumulation in TMEM; measured max relative error 2e-4 at K = 20000. */
+#define SS_PRECISION_F64 0u
+#define SS_PRECISION_TF32 (1u << 4)
+#define SS_PRECISION_MASK (15u << 4)
+
 /* ss_gemm_f64 operand form of A */
 #define SS_OP_N 0 /* A is M x K column-major (m contiguous)            : C = A  * B */
 #define SS_OP_T 1 /* A is stored K x M column-major (k contiguous)     : C = A' * B */
@@ -140,6 +148,10 @@ SS_API int32_t ss_spread_rows(ss_ctx* ctx, const ss_mat* G, const ss_ivec* k, ss
  * B is K x N column-major. */
 SS_API int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
                     const ss_ivec* row_div, const ss_ivec* col_flag);
+/* Same contract as ss_gemm_f64 (FP64 operands in, FP64 C out) with the product computed by
+ * tcgen05.mma kind::tf32 (accumulators in TMEM): precision = SS_PRECISION_TF32. */
+SS_API int32_t ss_gemm_lowp(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
+                            const ss_ivec* row_div, const ss_ivec* col_flag, uint32_t precision);
 /* Fused GEMM + all-gather for the multi-GPU chain: as ss_gemm_f64, and every element of C is also
  * stored, from the epilogue, to `n_mirrors` (<= 7) peer-GPU matrices with the same leading dimension
  * (`mirrors[i]` = device address, mapped into this process, of the peer's element C(0,0)) over

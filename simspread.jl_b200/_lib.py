@@ -16,6 +16,7 @@ P = C.POINTER
 SS_OK, SS_ERR_INVALID, SS_ERR_CUDA, SS_ERR_NO_DEVICE, SS_ERR_ASSERT, SS_ERR_OOM, SS_ERR_UNSUPPORTED = range(7)
 SS_PREDICT_CLEAN = 1
 SS_OP_N, SS_OP_T = 0, 1
+SS_PRECISION_F64, SS_PRECISION_TF32 = 0, 1 << 4
 
 
 class SimSpreadError(RuntimeError):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "ss_k_rows": (c_i32, [vp, vp, vp]),
     "ss_spread_rows": (c_i32, [vp, vp, vp, vp]),
     "ss_gemm_f64": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp]),
+    "ss_gemm_lowp": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp, c_u32]),
     "ss_gemm_f64_mirrored": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp, c_i32, P(vp)]),
     "ss_mat_ipc_handle": (c_i32, [vp, vp, vp]),
     "ss_ipc_open": (c_i32, [vp, vp, P(vp)]),

@@ -484,6 +484,34 @@ int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, 
     return SS_OK;
 }
 
+// dispatch of one chain product on the requested precision
+static int32_t chain_gemm(ss_ctx* ctx, uint32_t precision, int opA, const double* A, int64_t lda, const double* B,
+                          int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div,
+                          const int32_t* col_flag) {
+    if (precision == SS_PRECISION_F64)
+        return launch_gemm_f64(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
+    if (precision == SS_PRECISION_TF32)
+        return launch_gemm_tf32(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
+    set_error("unknown precision flag 0x%x", precision);
+    return SS_ERR_INVALID;
+}
+
+int32_t ss_gemm_lowp(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C, const ss_ivec* row_div,
+                     const ss_ivec* col_flag, uint32_t precision) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(A && B && C, "ss_gemm_lowp: null matrix");
+    SS_REQUIRE(opA == SS_OP_N || opA == SS_OP_T, "ss_gemm_lowp: bad opA");
+    const int64_t M = (opA == SS_OP_N) ? A->rows : A->cols;
+    const int64_t K = (opA == SS_OP_N) ? A->cols : A->rows;
+    SS_REQUIRE(B->rows == K && C->rows == M && C->cols == B->cols, "ss_gemm_lowp: shape mismatch");
+    SS_REQUIRE(!row_div || row_div->n == M, "ss_gemm_lowp: row_div has wrong length");
+    SS_REQUIRE(!col_flag || col_flag->n == B->cols, "ss_gemm_lowp: col_flag has wrong length");
+    SS_TRY(chain_gemm(ctx, precision & SS_PRECISION_MASK, opA, A->d, A->ld, B->d, B->ld, C->d, C->ld, M, B->cols, K,
+                      row_div ? row_div->d : nullptr, col_flag ? col_flag->d : nullptr));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
 int32_t ss_gemm_f64_mirrored(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
                              const ss_ivec* row_div, const ss_ivec* col_flag, int32_t n_mirrors, void* const* mirrors) {
     SS_ENTER(ctx);
@@ -542,7 +570,8 @@ struct ChainWs {
     int64_t ldt = 0;
 };
 
-static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ChainWs* w) {
+static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ChainWs* w,
+                           uint32_t precision = SS_PRECISION_F64) {
     const int64_t ns = Y->rows, nt = Y->cols, nf = Xs ? Xs->cols : 0;
     void* p;
     const size_t kbytes = size_t(round_up(ns, 64) + round_up(nf, 64) + round_up(nt, 64)) * 4;
@@ -560,8 +589,8 @@ static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, Chain
         SS_TRY(scratch_get(ctx, 2, size_t(w->ldt) * size_t(nt) * 8, &p));
         w->T = static_cast<double*>(p);
         // T[f,t] = (sum_s Xs[s,f] * Wst[s,t]) / kf[f]
-        SS_TRY(launch_gemm_f64(ctx, SS_OP_T, Xs->d, Xs->ld, w->Wst, w->ldw, w->T, w->ldt, nf, nt, ns, w->kf,
-                               nullptr, false));
+        SS_TRY(chain_gemm(ctx, precision, SS_OP_T, Xs->d, Xs->ld, w->Wst, w->ldw, w->T, w->ldt, nf, nt, ns, w->kf,
+                          nullptr));
     }
     return SS_OK;
 }
@@ -581,9 +610,10 @@ int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const 
         return SS_OK;
     }
     ChainWs w;
-    SS_TRY(chain_front(ctx, Xs, Y, &w));
-    SS_TRY(launch_gemm_f64(ctx, SS_OP_N, Xq->d, Xq->ld, w.T, w.ldt, R->d, R->ld, Xq->rows, Y->cols, Xq->cols,
-                           nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr, false));
+    const uint32_t prec = flags & SS_PRECISION_MASK;
+    SS_TRY(chain_front(ctx, Xs, Y, &w, prec));
+    SS_TRY(chain_gemm(ctx, prec, SS_OP_N, Xq->d, Xq->ld, w.T, w.ldt, R->d, R->ld, Xq->rows, Y->cols, Xq->cols,
+                      nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr));
     if (kt_out)
         SS_CHECK_CUDA(cudaMemcpyAsync(kt_out->d, w.kt, size_t(Y->cols) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

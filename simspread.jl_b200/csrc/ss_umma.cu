@@ -1,0 +1,453 @@
+// tcgen05 (5th-generation tensor core) form of the chain-product GEMM: the opt-in reduced-precision
+// modes of predict.  The reference's only GPU mode (`GPU=true`, src/core.jl:404,411-413) silently
+// computes `A * W^2` in Float32 through cuBLAS SGEMM; here the same products run on tcgen05.mma
+// kind::tf32 with accumulators in TMEM:
+//
+//   SS_PRECISION_TF32 : one pass, operands rounded to TF32 (10-bit mantissa), FP32 accumulation.
+//   (A 3xTF32 split -- hi*hi + hi*lo + lo*hi, the `split` argument below -- was measured too: the
+//   in-TMEM FP32 accumulation truncates, so at K = 20000 the split result (3.3e-4) is no better than
+//   the single pass (1.9e-4) at 3x the cost; it is therefore not exposed through the ABI.)
+//
+// Structure (one CTA per SM, persistent over 128x256 C tiles):
+//   warp 0  TMA producer : cp.async.bulk.tensor of K-major, SWIZZLE_128B operand slabs (A 128 rows,
+//                          B 256 rows, 128 bytes of K per slab) into a 4-stage smem ring
+//   warp 1  MMA issuer   : one lane issues tcgen05.mma (M=128, N=256, 32 bytes of K per instruction)
+//                          from smem descriptors; tcgen05.commit releases the smem stage / publishes
+//                          the accumulator
+//   warp 2  TMEM owner   : tcgen05.alloc of all 512 columns = two 128x256 FP32 accumulators, so the
+//                          epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 4-7 epilogue   : tcgen05.ld (32 lanes x 32 columns per instruction) -> FP64 -> fused
+//                          normalisation (/kf, clean! flag) -> column-major C
+// Operand pairs (A_p, B_p) are concatenated along K, which is how the 3xTF32 passes (and, later,
+// integer slices) share one accumulator.
+#include <cuda.h>
+
+#include "ss_common.cuh"
+
+namespace {
+
+constexpr int UM = 128, UN = 256;
+constexpr int U_STAGES = 4;
+constexpr int A_ST_BYTES = UM * 128;  // 16 KB
+constexpr int B_ST_BYTES = UN * 128;  // 32 KB
+constexpr int ST_BYTES = A_ST_BYTES + B_ST_BYTES;
+constexpr int U_THREADS = 256;
+constexpr int MAXP = 4;
+constexpr int U_GROUP_M = 8;
+constexpr size_t U_SMEM = size_t(U_STAGES) * ST_BYTES + 1024 + 256;
+
+struct UmmaMaps {
+    CUtensorMap a[MAXP];
+    CUtensorMap b[MAXP];
+};
+
+struct UmmaParams {
+    int M, N;
+    int npairs;
+    int kslabs;  // 128-byte K slabs per operand pair
+    int bke;     // elements per slab
+    int tiles_m, tiles_n;
+    uint32_t idesc;
+    double* C;
+    int64_t ldc;
+    const int32_t* row_div;
+    const int32_t* col_flag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "UWAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni UWAIT_DONE;\n"
+        "bra.uni UWAIT_LOOP;\n"
+        "UWAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 8 rows * 128 B |
+// version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct UTile {
+    int tm, tn;
+};
+__device__ __forceinline__ UTile utile(int tile, int tiles_m, int tiles_n) {
+    const int group_size = U_GROUP_M * tiles_n;
+    const int gid = tile / group_size;
+    const int first_m = gid * U_GROUP_M;
+    const int gm = min(tiles_m - first_m, U_GROUP_M);
+    const int r = tile - gid * group_size;
+    return {first_m + r % gm, r / gm};
+}
+
+__global__ void __launch_bounds__(U_THREADS, 1)
+    ss_umma_tf32_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+    extern __shared__ uint8_t usmem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t smem_base = (smem_u32(usmem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + U_STAGES * ST_BYTES;
+    // barriers: full[U_STAGES], empty[U_STAGES], tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * U_STAGES;
+    const uint32_t bar_tfull = bar_base + 16 * U_STAGES, bar_tempty = bar_tfull + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < U_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const UTile tc = utile(tile, p.tiles_m, p.tiles_n);
+                const int m0 = tc.tm * UM, n0 = tc.tn * UN;
+                for (int pr = 0; pr < p.npairs; ++pr)
+                    for (int kb = 0; kb < p.kslabs; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, ST_BYTES);
+                        const uint32_t sA = smem_base + stage * ST_BYTES;
+                        tma_load_2d(sA, &maps.a[pr], kb * p.bke, m0, bar_full + 8 * stage);
+                        tma_load_2d(sA + A_ST_BYTES, &maps.b[pr], kb * p.bke, n0, bar_full + 8 * stage);
+                        if (++stage == U_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * UN;
+                uint32_t accumulate = 0;
+                const int nslab = p.npairs * p.kslabs;
+                for (int s = 0; s < nslab; ++s) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + stage * ST_BYTES;
+                    const uint64_t adesc = make_kmajor_desc(sA);
+                    const uint64_t bdesc = make_kmajor_desc(sA + A_ST_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte slab
+                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
+                    if (++stage == U_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * as);  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const UTile tc = utile(tile, p.tiles_m, p.tiles_n);
+            const int m0 = tc.tm * UM, n0 = tc.tn * UN;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const int row = m0 + 32 * ew + lane;
+            const uint32_t taddr = tmem_base + (uint32_t(32 * ew) << 16) + as * UN;
+            double inv = 1.0;
+            bool zero_row = false;
+            if (p.row_div && row < p.M) {
+                const int d = __ldg(p.row_div + row);
+                zero_row = (d == 0);
+                inv = double(d);
+            }
+#pragma unroll 1
+            for (int c = 0; c < UN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c * 32 + j;
+                        if (col < p.N) {
+                            double v = double(__uint_as_float(r[j]));
+                            if (p.row_div) v = zero_row ? 0.0 : v / inv;
+                            if (p.col_flag && __ldg(p.col_flag + col) == 0) v = -99.0;
+                            p.C[int64_t(col) * p.ldc + row] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- FP64 -> TF32 operand preparation ---------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t o;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(x));
+    return __uint_as_float(o);
+}
+
+// src: column-major FP64 with K contiguous (element (k, j) at src[j*ld + k]) -> dst[j][k] float,
+// row pitch kp.  hi = tf32(x); lo (optional) = tf32(float(x) - hi).
+__global__ void __launch_bounds__(256)
+    cvt_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, float* __restrict__ hi,
+                      float* __restrict__ lo, int64_t kp) {
+    const int64_t k = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (k >= kp) return;
+    for (int64_t j = blockIdx.y; j < J; j += gridDim.y) {
+        const float x = (k < K) ? float(src[j * ld + k]) : 0.f;
+        const float h = to_tf32(x);
+        hi[j * kp + k] = h;
+        if (lo) lo[j * kp + k] = to_tf32(x - h);
+    }
+}
+
+// src: column-major FP64 with M contiguous (element (m, k) at src[k*ld + m]) -> dst[m][k] float
+__global__ void __launch_bounds__(256)
+    cvt_transpose_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, float* __restrict__ hi,
+                         float* __restrict__ lo, int64_t kp) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t m0 = int64_t(blockIdx.x) * 32, k0 = int64_t(blockIdx.y) * 32;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t m = m0 + tx, k = k0 + j;
+        tile[j][tx] = (m < M && k < K) ? float(src[k * ld + m]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t m = m0 + j, k = k0 + tx;
+        if (m < M && k < kp) {
+            const float x = tile[tx][j];
+            const float h = to_tf32(x);
+            hi[m * kp + k] = h;
+            if (lo) lo[m * kp + k] = to_tf32(x - h);
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// K-major FP32 operand: rows x K floats, row pitch kp floats; box = 32 floats (128 B) x box_rows
+int32_t make_map_f32(CUtensorMap* map, const float* base, int64_t K, int64_t rows, int64_t kp, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        ss::set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SS_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(rows)};
+    cuuint64_t gstride[1] = {cuuint64_t(kp) * 4};
+    cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ss::set_error("cuTensorMapEncodeTiled (f32) failed with CUresult %d", int(r));
+        return SS_ERR_CUDA;
+    }
+    return SS_OK;
+}
+
+}  // namespace
+
+namespace ss {
+
+// C (FP64, column-major, M x N) = op(A) * B in TF32 (split == false) or 3xTF32 (split == true).
+// opA / operand layouts as launch_gemm_f64.  Scratch slots 14 (A) and 15 (B) hold the converted operands.
+int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                         int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
+                         bool split) {
+    SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tf32: empty problem");
+    SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_tf32: dimension too large");
+    const int64_t kp = round_up(K, 32);
+    const int nbuf = split ? 2 : 1;
+    void* p;
+    SS_TRY(scratch_get(ctx, 14, size_t(M) * kp * 4 * nbuf, &p));
+    float* Ahi = static_cast<float*>(p);
+    float* Alo = split ? Ahi + M * kp : nullptr;
+    SS_TRY(scratch_get(ctx, 15, size_t(N) * kp * 4 * nbuf, &p));
+    float* Bhi = static_cast<float*>(p);
+    float* Blo = split ? Bhi + N * kp : nullptr;
+    auto gy = [&](int64_t gx, int64_t n) {
+        int64_t want = ceil_div(int64_t(ctx->sm_count) * 16, gx);
+        if (want < 1) want = 1;
+        if (want > n) want = n;
+        if (want > 65535) want = 65535;
+        return unsigned(want);
+    };
+    if (opA == SS_OP_N) {
+        dim3 g{unsigned(ceil_div(M, 32)), unsigned(ceil_div(kp, 32))};
+        SS_REQUIRE(g.y <= 65535, "gemm_tf32: K too large for the transpose grid");
+        cvt_transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, Ahi, Alo, kp);
+    } else {
+        const int64_t gx = ceil_div(kp, 256);
+        dim3 g{unsigned(gx), gy(gx, M)};
+        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, Ahi, Alo, kp);
+    }
+    {
+        const int64_t gx = ceil_div(kp, 256);
+        dim3 g{unsigned(gx), gy(gx, N)};
+        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, Bhi, Blo, kp);
+    }
+    ctx->launches += 2;
+    SS_CHECK_CUDA(cudaGetLastError());
+
+    UmmaMaps maps;
+    UmmaParams q{};
+    q.npairs = split ? 3 : 1;
+    const float* ap[3] = {Ahi, Ahi, Alo};  // hi*hi, hi*lo, lo*hi
+    const float* bp[3] = {Bhi, Blo, Bhi};
+    for (int i = 0; i < q.npairs; ++i) {
+        SS_TRY(make_map_f32(&maps.a[i], ap[i], K, M, kp, UM));
+        SS_TRY(make_map_f32(&maps.b[i], bp[i], K, N, kp, UN));
+    }
+    for (int i = q.npairs; i < MAXP; ++i) {
+        maps.a[i] = maps.a[0];
+        maps.b[i] = maps.b[0];
+    }
+    q.M = int(M);
+    q.N = int(N);
+    q.kslabs = int(kp / 32);
+    q.bke = 32;
+    q.tiles_m = int(ceil_div(M, UM));
+    q.tiles_n = int(ceil_div(N, UN));
+    // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2) [10,13) |
+    // a_major K (0) [15] | b_major K (0) [16] | N>>3 [17,23) | M>>4 [24,29)
+    q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(UN >> 3) << 17) | (uint32_t(UM >> 4) << 24);
+    q.C = C;
+    q.ldc = ldc;
+    q.row_div = row_div;
+    q.col_flag = col_flag;
+    const int64_t total = int64_t(q.tiles_m) * q.tiles_n;
+    const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);
+    SS_CHECK_CUDA(cudaFuncSetAttribute(ss_umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(U_SMEM)));
+    ss_ctx::ProfRec rec{nullptr, nullptr, 2.0 * double(M) * double(N) * double(K)};
+    if (ctx->profile) {
+        SS_CHECK_CUDA(cudaEventCreate(&rec.start));
+        SS_CHECK_CUDA(cudaEventCreate(&rec.stop));
+        SS_CHECK_CUDA(cudaEventRecord(rec.start, ctx->stream));
+    }
+    ss_umma_tf32_kernel<<<grid, U_THREADS, U_SMEM, ctx->stream>>>(maps, q);
+    SS_CHECK_CUDA(cudaGetLastError());
+    if (ctx->profile) {
+        SS_CHECK_CUDA(cudaEventRecord(rec.stop, ctx->stream));
+        ctx->prof.push_back(rec);
+    }
+    ctx->launches++;
+    return SS_OK;
+}
+
+}  // namespace ss

@@ -453,16 +453,24 @@ def _dense_predict(A: NamedArray, B: NamedArray, rows, cols) -> NamedArray:
     return Fn[list(rows), list(cols)]
 
 
-def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto") -> NamedArray:
+_PRECISION_FLAGS = {"f64": _lib.SS_PRECISION_F64, "tf32": _lib.SS_PRECISION_TF32}
+
+
+def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
+            precision: str = "f64") -> NamedArray:
     """`predict((A, B), ytest)`, `predict(A, B, ytest)` (reference src/core.jl:402-425) and
     `predict(A, ytrain)` (:446-466).  Returns `F[names(ytest,1), names(ytest,2)]`.
 
     `GPU` is accepted for signature compatibility: this implementation always runs on the GPU, in
     Float64 (the reference's GPU=true silently drops to Float32, src/core.jl:404).  `clean=True`
-    (extension) fuses `clean!` into the product's epilogue.  `layout` (extension) selects the dense
+    (extension) fuses `clean!` into the product's epilogue.  `precision` (extension): "f64" (default,
+    DMMA) or "tf32" (tcgen05.mma kind::tf32 with FP32 accumulation in TMEM -- the fast, reduced
+    precision analogue of the reference's Float32 GPU mode; relative error ~2e-4).  `layout` (extension) selects the dense
     DMMA chain, the sparse row-split SpMM chain, or picks by the density of the feature blocks."""
     if layout not in ("auto", "dense", "sparse"):
         raise ValueError("layout must be 'auto', 'dense' or 'sparse'")
+    if precision not in _PRECISION_FLAGS:
+        raise ValueError("precision must be 'f64' (default) or 'tf32' (tcgen05, opt-in)")
     ctx = Context.default()
     if len(args) == 2 and isinstance(args[0], tuple):
         (A, B), yq = args
@@ -479,7 +487,9 @@ def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto")
         Bn = B.to_named() if isinstance(B, Graph) else B
         return _dense_predict(An, Bn, rows, cols)
     g = A
-    flags = SS_PREDICT_CLEAN if clean else 0
+    flags = (SS_PREDICT_CLEAN if clean else 0) | _PRECISION_FLAGS[precision]
+    if precision != "f64" and layout == "auto":
+        layout = "dense"  # the reduced-precision modes exist for the dense tensor-core chain only
     qpos = {n: i for i, n in enumerate(g.queries)}
     spos = {n: i for i, n in enumerate(g.sources)}
     tpos = {n: i for i, n in enumerate(g.targets)}

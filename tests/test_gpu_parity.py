@@ -596,3 +596,50 @@ def test_predict_layout_auto_switch(ss, o):
         want = o.predict_dense(Ao, Bo, nn, q, tn)
         for got in (auto, dense, sparse):
             assert relerr(got.array, want) < RTOL
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (129, 257, 33), (300, 520, 260), (45, 664, 400), (1000, 1500, 2000)])
+@pytest.mark.parametrize("op", ["N", "T"])
+def test_gemm_tf32_tcgen05(ss, M, N, K, op):
+    """Opt-in tcgen05 path: exact on operands that are exactly representable in TF32 (a descriptor or
+    pipeline bug cannot hide behind rounding), and within the stated TF32 bound on real data."""
+    from simspread_b200._lib import SS_OP_N, SS_OP_T, SS_PRECISION_TF32, check
+    rng = np.random.default_rng(M + 3 * N + 5 * K)
+    ctx = ss.Context.default()
+    o_ = SS_OP_N if op == "N" else SS_OP_T
+    A = rng.integers(-3, 4, size=(M, K)).astype(float)
+    B = rng.integers(-3, 4, size=(K, N)).astype(float)
+    div = rng.integers(0, 3, size=M).astype(np.int32)
+    flag = rng.integers(0, 2, size=N).astype(np.int32)
+    dA, dB, dC = ss.DMat.from_host(ctx, A if op == "N" else A.T), ss.DMat.from_host(ctx, B), ss.DMat(ctx, M, N)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, None, None, SS_PRECISION_TF32))
+    assert np.array_equal(dC.to_host(), A @ B)
+    dd, df = ss.DIVec.from_host(ctx, div), ss.DIVec.from_host(ctx, flag)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, dd.h, df.h, SS_PRECISION_TF32))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = np.where(div[:, None] == 0, 0.0, (A @ B) / div[:, None].astype(float))
+    ref[:, flag == 0] = -99.0
+    assert np.allclose(dC.to_host(), ref, rtol=1e-6, atol=0)
+    A, B = rng.random((M, K)), rng.random((K, N))
+    dA, dB = ss.DMat.from_host(ctx, A if op == "N" else A.T), ss.DMat.from_host(ctx, B)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, None, None, SS_PRECISION_TF32))
+    assert np.max(np.abs(dC.to_host() - A @ B) / (A @ B)) < 2e-3  # TF32: 10-bit mantissa operands
+
+
+def test_predict_tf32_mode_against_oracle(ss, o):
+    S, Yfull = _enzyme_like(o, seed=5)
+    N, Nt = Yfull.shape
+    names = [f"D{i:04d}" for i in range(N)]
+    tn = [f"T{j:04d}" for j in range(Nt)]
+    DT = ss.NamedArray(Yfull, (names, tn))
+    X = ss.featurize(ss.NamedArray(S, (names, names)), 0.2, True)
+    q = names[::9]
+    A, B = ss.construct(DT, X, q)
+    got = ss.predict((A, B), DT[q, tn], precision="tf32", clean=True)
+    exact = ss.predict((A, B), DT[q, tn], clean=True)
+    nz = (exact.array != 0) & (exact.array != -99)
+    assert np.array_equal(got.array == -99, exact.array == -99)
+    assert np.max(np.abs(got.array[nz] - exact.array[nz]) / exact.array[nz]) < 2e-3  # stated TF32 bound
+    assert np.array_equal(got.array[exact.array == 0], exact.array[exact.array == 0])
+    with pytest.raises(ValueError):
+        ss.predict((A, B), DT[q, tn], precision="f16")
