@@ -211,6 +211,16 @@ SS_API int32_t ss_auroc_auprc(ss_ctx* ctx, const void* labels_u8_dev, const void
 /* Same for the entries of two device matrices (Ytrue != 0 is the label), column-major order. */
 SS_API int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, double* out2);
 
+/* BEDROC [src/performance.jl:22-38] over the entries of two device matrices (label = Ytrue == 1):
+ * stable descending radix sort (ascending when rev == 0), sum of exp(-alpha*rank/N) over the
+ * positives, closed-form normalisation. */
+SS_API int32_t ss_bedroc(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t rev, double alpha, double* out);
+/* maxperformance / meanperformance / meanstdperformance [src/performance.jl:425-531] of one
+ * confusion-matrix metric over all unique-score thresholds (MLBase.roc semantics):
+ * metric: 0 f1score, 1 mcc, 2 accuracy, 3 balancedaccuracy, 4 recall, 5 precision.
+ * out[0] = maximum, out[1] = mean, out[2] = corrected sample std, out[3] = number of thresholds. */
+SS_API int32_t ss_threshold_sweep(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t metric, double* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,9 +11,9 @@ The directory is called `simspread.jl_b200` (not an importable identifier); impo
 from ._lib import SimSpreadError, header_symbols, lib  # noqa: F401
 from .namedarray import NamedArray  # noqa: F401
 from .host import (  # noqa: F401
-    AuPRC, AuROC, Context, alpha_sweep, cross_validate, DCsr, DIVec, DMat, Graph, accuracy, balancedaccuracy, clean_, construct, cutoff,
-    cutoff_, f1score, featurize, featurize_, k, mcc, precision, precisionatL, predict, recall,
-    recallatL, split, spread, validity_ratio,
+    AuPRC, AuROC, BEDROC, Context, alpha_sweep, cross_validate, DCsr, DIVec, DMat, Graph, accuracy, balancedaccuracy, clean_, construct, cutoff,
+    cutoff_, f1score, featurize, featurize_, k, mcc, maxperformance, meanperformance, meanstdperformance, precision, precisionatL, predict, recall,
+    recallatL, save, split, spread, validity_ratio,
 )
 from ._build import build, lib_path  # noqa: F401
 

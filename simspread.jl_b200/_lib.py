@@ -81,6 +81,8 @@ SIGNATURES = {
     "ss_atl": (c_i32, [vp, vp, vp, c_i32, P(c_f64)]),
     "ss_auroc_auprc": (c_i32, [vp, vp, vp, c_i64, P(c_f64)]),
     "ss_auroc_auprc_mat": (c_i32, [vp, vp, vp, P(c_f64)]),
+    "ss_bedroc": (c_i32, [vp, vp, vp, c_i32, c_f64, P(c_f64)]),
+    "ss_threshold_sweep": (c_i32, [vp, vp, vp, c_i32, P(c_f64)]),
 }
 
 _lib = None

@@ -828,4 +828,25 @@ int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, do
     return auroc_auprc_mat(ctx, Ytrue, R, out2);
 }
 
+int32_t ss_bedroc(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t rev, double alpha, double* out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Ytrue && R && out, "ss_bedroc: null argument");
+    if (Ytrue->rows != R->rows || Ytrue->cols != R->cols) {
+        set_error("The number of scores must be equal to the number of labels");
+        return SS_ERR_ASSERT;
+    }
+    return bedroc(ctx, Ytrue, R, rev, alpha, out);
+}
+
+int32_t ss_threshold_sweep(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t metric, double* out4) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Ytrue && R && out4, "ss_threshold_sweep: null argument");
+    SS_REQUIRE(metric >= 0 && metric <= 5, "ss_threshold_sweep: unknown metric %d", metric);
+    if (Ytrue->rows != R->rows || Ytrue->cols != R->cols) {
+        set_error("The number of scores must be equal to the number of labels");
+        return SS_ERR_ASSERT;
+    }
+    return threshold_sweep(ctx, Ytrue, R, metric, out4);
+}
+
 }  // extern "C"

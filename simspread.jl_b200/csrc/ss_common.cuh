@@ -121,5 +121,7 @@ int32_t atl(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int L, double* out2);
 int32_t auroc_auprc(ss_ctx* ctx, const uint8_t* labels, const double* scores, int64_t M,
                     double* out2);
 int32_t auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, double* out2);
+int32_t threshold_sweep(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int metric, double* out4);
+int32_t bedroc(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int rev, double alpha, double* out);
 
 }  // namespace ss

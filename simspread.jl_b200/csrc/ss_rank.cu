@@ -77,6 +77,111 @@ __global__ void __launch_bounds__(TOPL_TPB)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-level top-L (L <= 32).  A block owns 32 consecutive rows: column chunks are loaded with lanes
+// along the rows (coalesced for the column-major R), transposed through shared memory, and each warp
+// then scans ITS rows with lanes along the columns.  The sorted list of a row lives across the lanes
+// of the warp (lane i = rank i); a chunk is filtered with one compare + ballot against the current
+// L-th key, and the rare survivors are inserted with a popc rank and one shuffle.  Candidates are
+// taken in ascending column order and equal keys never displace an earlier column, which is exactly
+// the stable descending order of `sortperm(row; rev=true)`.
+// ------------------------------------------------------------------------------------------------
+constexpr int WT_ROWS = 32;
+constexpr int WT_COLS = 256;
+constexpr int WT_TPB = 256;  // 8 warps, 4 rows each
+
+__device__ __forceinline__ double key_to_value(uint64_t k) {
+    if (k == 0xFFFFFFFFFFFFFFFFull) return __longlong_as_double(0x7ff8000000000000ll);
+    const uint64_t b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(WT_TPB)
+    topl_warp_kernel(const double* __restrict__ R, int64_t rows, int64_t cols, int64_t ld, int L,
+                     int32_t* __restrict__ idx_out, double* __restrict__ val_out, int64_t ldv) {
+    extern __shared__ double wt_tile[];  // [WT_ROWS][WT_COLS + 1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = int64_t(blockIdx.x) * WT_ROWS;
+    // per-warp state of its 4 rows: lane i holds the i-th best (key, column); cnt = entries so far
+    uint64_t lkey[4];
+    int32_t lidx[4];
+    int cnt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        lkey[q] = 0;
+        lidx[q] = -1;
+        cnt[q] = 0;
+    }
+    for (int64_t c0 = 0; c0 < cols; c0 += WT_COLS) {
+        const int nc = int(min(int64_t(WT_COLS), cols - c0));
+        __syncthreads();
+        // load: warp w takes columns w, w+8, ...; lane = row (256 B contiguous per column)
+#pragma unroll 8
+        for (int cc = warp; cc < WT_COLS; cc += WT_TPB / 32) {
+            const int64_t r = row0 + lane;
+            if (cc < nc && r < rows) wt_tile[lane * (WT_COLS + 1) + cc] = __ldg(R + (c0 + cc) * ld + r);
+        }
+        __syncthreads();
+        // the four rows of this warp are independent chains: issue their loads / ballots together
+        uint64_t thr[4];
+        bool full[4], live[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            thr[q] = __shfl_sync(0xffffffffu, lkey[q], L - 1);  // key of rank L-1 once the list is full
+            full[q] = cnt[q] >= L;
+            live[q] = row0 + 4 * warp + q < rows;               // warp-uniform
+        }
+        for (int cb = 0; cb < nc; cb += 32) {
+            const int c = cb + lane;
+            const bool inb = c < nc;
+            uint64_t key[4];
+            unsigned cand[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                key[q] = (inb && live[q]) ? isless_key(wt_tile[(4 * warp + q) * (WT_COLS + 1) + c]) : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                cand[q] = __ballot_sync(0xffffffffu, inb && live[q] && (!full[q] || key[q] > thr[q]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!cand[q]) continue;  // the common case after the first few hundred columns
+                unsigned cd = cand[q];
+                while (cd) {
+                    const int src = __ffs(cd) - 1;
+                    cd &= cd - 1;
+                    const uint64_t ck = __shfl_sync(0xffffffffu, key[q], src);
+                    const int32_t ci = int32_t(c0 + cb + src);
+                    // rank = number of list entries with key >= ck (earlier columns win ties)
+                    const bool ge = (lane < cnt[q]) && (lkey[q] >= ck);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, ge));
+                    if (pos >= L) continue;  // no longer qualifies after earlier inserts of this chunk
+                    const uint64_t upk = __shfl_up_sync(0xffffffffu, lkey[q], 1);
+                    const int32_t upi = __shfl_up_sync(0xffffffffu, lidx[q], 1);
+                    if (lane == pos) {
+                        lkey[q] = ck;
+                        lidx[q] = ci;
+                    } else if (lane > pos) {
+                        lkey[q] = upk;
+                        lidx[q] = upi;
+                    }
+                    if (cnt[q] < L) ++cnt[q];
+                }
+                thr[q] = __shfl_sync(0xffffffffu, lkey[q], L - 1);
+                full[q] = cnt[q] >= L;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t row = row0 + 4 * warp + q;
+        if (row < rows && lane < L) {
+            const bool have = lane < cnt[q];
+            idx_out[row * L + lane] = have ? lidx[q] : -1;
+            if (val_out) val_out[row * ldv + lane] = have ? key_to_value(lkey[q]) : 0.0;
+        }
+    }
+}
+
 // recall@L / precision@L per row from the top-L index lists (src/performance.jl:315-327,377-384):
 // Xi = sum(y), Xi_L = sum(first(y[order], L)).
 constexpr int ATL_TPB = 128;
@@ -180,46 +285,82 @@ __global__ void __launch_bounds__(RS_TPB)
     hist[int64_t(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// single-block exclusive scan of n uint32 counts (n = 256 * nblocks), 64-bit running sum stored as
-// uint64 offsets
+// exclusive scan of every digit row of hist[digit][block] (one block per digit, coalesced, running
+// carry) -> per-(digit, block) offset relative to the digit's start + digit totals
 __global__ void __launch_bounds__(1024)
-    rs_scan_kernel(const uint32_t* __restrict__ in, int64_t n, uint64_t* __restrict__ out) {
-    __shared__ unsigned long long part[1024];
-    const int t = threadIdx.x;
-    const int64_t chunk = (n + 1023) / 1024;
-    const int64_t b = t * chunk, e = min(n, b + chunk);
-    unsigned long long s = 0;
-    for (int64_t i = b; i < e; ++i) s += in[i];
-    part[t] = s;
+    rs_scan_rows_kernel(const uint32_t* __restrict__ hist, int64_t nblocks, uint32_t* __restrict__ rel,
+                        unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    const int d = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t* in = hist + int64_t(d) * nblocks;
+    uint32_t* out = rel + int64_t(d) * nblocks;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    if (t == 0) {
+    for (int64_t i0 = 0; i0 < nblocks; i0 += 1024) {
+        const int64_t i = i0 + t;
+        const unsigned long long v = (i < nblocks) ? in[i] : 0;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        unsigned long long wpre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            if (w == warp) wpre = tot;
+            tot += wsum[w];
+        }
+        const unsigned long long carry = carry_s;
+        if (i < nblocks) out[i] = uint32_t(carry + wpre + inc - v);
+        __syncthreads();
+        if (t == 0) carry_s = carry + tot;
+    }
+    __syncthreads();
+    if (t == 0) totals[d] = carry_s;
+}
+
+// exclusive scan of the 256 digit totals -> global start of every digit
+__global__ void __launch_bounds__(256)
+    rs_scan_totals_kernel(const unsigned long long* __restrict__ totals, unsigned long long* __restrict__ base) {
+    __shared__ unsigned long long s[256];
+    s[threadIdx.x] = totals[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
         unsigned long long run = 0;
-        for (int i = 0; i < 1024; ++i) {
-            const unsigned long long v = part[i];
-            part[i] = run;
+        for (int i = 0; i < 256; ++i) {
+            const unsigned long long v = s[i];
+            s[i] = run;
             run += v;
         }
     }
     __syncthreads();
-    unsigned long long run = part[t];
-    for (int64_t i = b; i < e; ++i) {
-        out[i] = run;
-        run += in[i];
-    }
+    base[threadIdx.x] = s[threadIdx.x];
 }
 
-// stable scatter: rank inside the warp by __match_any_sync, across warps by a per-digit prefix
+// stable scatter: rank inside the warp by __match_any_sync, across warps by a per-digit prefix; the
+// tile is first ordered by digit in shared memory so that the global stores of one digit run are
+// contiguous (coalesced) instead of one scattered 8-byte store per key.
 __global__ void __launch_bounds__(RS_TPB)
     rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint8_t* __restrict__ lab_in, int64_t M, int shift,
-                        const uint64_t* __restrict__ offsets, int64_t nblocks, uint64_t* __restrict__ keys_out,
-                        uint8_t* __restrict__ lab_out) {
-    __shared__ unsigned int wcount[RS_TPB / 32][256];
-    __shared__ unsigned long long dbase[256];
+                        const uint32_t* __restrict__ rel, const unsigned long long* __restrict__ base, int64_t nblocks,
+                        uint64_t* __restrict__ keys_out, uint8_t* __restrict__ lab_out) {
+    extern __shared__ uint8_t rs_smem[];
+    uint64_t* skey = reinterpret_cast<uint64_t*>(rs_smem);                      // [RS_TILE]
+    unsigned int(*wcount)[256] = reinterpret_cast<unsigned int(*)[256]>(skey + RS_TILE);  // [8][256]
+    unsigned long long* gbase = reinterpret_cast<unsigned long long*>(wcount + RS_TPB / 32);  // [256]
+    unsigned int* dstart = reinterpret_cast<unsigned int*>(gbase + 256);        // [256]
+    unsigned int* wtot = dstart + 256;                                          // [8]
+    uint8_t* slab = reinterpret_cast<uint8_t*>(wtot + 8);                       // [RS_TILE]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (RS_TPB / 32) * 256; i += RS_TPB) (&wcount[0][0])[i] = 0;
     __syncthreads();
     // order inside the tile: (warp, item, lane) == ascending index
-    const int64_t wbase = int64_t(blockIdx.x) * RS_TILE + int64_t(warp) * (32 * RS_ITEMS);
+    const int64_t tbase = int64_t(blockIdx.x) * RS_TILE;
+    const int64_t wbase = tbase + int64_t(warp) * (32 * RS_ITEMS);
     uint64_t key[RS_ITEMS];
     uint8_t lab[RS_ITEMS];
     unsigned int rank[RS_ITEMS];
@@ -254,18 +395,39 @@ __global__ void __launch_bounds__(RS_TPB)
             wcount[w][d] = run;
             run += v;
         }
-        dbase[d] = offsets[int64_t(d) * nblocks + blockIdx.x];
+        gbase[d] = base[d] + rel[int64_t(d) * nblocks + blockIdx.x];
+        // exclusive scan of the 256 digit totals of this tile
+        unsigned int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        unsigned int wpre = 0;
+#pragma unroll
+        for (int w = 0; w < RS_TPB / 32; ++w)
+            if (w < warp) wpre += wtot[w];
+        dstart[d] = wpre + inc - run;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const int64_t idx = wbase + i * 32 + lane;
-        if (idx < M) {
-            const unsigned int d = (unsigned int)((key[i] >> shift) & 255);
-            const unsigned long long pos = dbase[d] + wcount[warp][d] + rank[i];
-            keys_out[pos] = key[i];
-            lab_out[pos] = lab[i];
-        }
+        const unsigned int d = (unsigned int)((key[i] >> shift) & 255);
+        const unsigned int pos = dstart[d] + wcount[warp][d] + rank[i];
+        skey[pos] = key[i];
+        slab[pos] = lab[i];
+    }
+    __syncthreads();
+    const int64_t rem = M - tbase;
+    const int count = int(rem < RS_TILE ? rem : RS_TILE);
+    for (int i = threadIdx.x; i < count; i += RS_TPB) {
+        const uint64_t k = skey[i];
+        const unsigned int d = (unsigned int)((k >> shift) & 255);
+        const unsigned long long g = gbase[d] + (unsigned int)(i - dstart[d]);
+        keys_out[g] = k;
+        lab_out[g] = slab[i];
     }
 }
 
@@ -456,16 +618,208 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
-int32_t sort_and_integrate(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB, uint8_t* labB, int64_t M,
-                           double* out2) {
+// ---- confusion-matrix metrics over every unique threshold (reference src/performance.jl:102-296,
+// ---- 425-531: maxperformance / meanperformance / meanstdperformance) ----------------------------
+enum { MET_F1 = 0, MET_MCC = 1, MET_ACC = 2, MET_BACC = 3, MET_RECALL = 4, MET_PRECISION = 5 };
+
+__device__ __forceinline__ double mcc_eps(double a, double b) {  // src/performance.jl:150-152
+    const double e = 2.2250738585072014e-308;                    // floatmin(Float64)
+    return (a * e - b * e) / sqrt((a + b) * (a + e) * (b + e) * (e + e));
+}
+
+__device__ double confusion_metric(int metric, long long tn, long long fp, long long fn, long long tp) {
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    switch (metric) {
+        case MET_F1: {
+            const double den = double(tp) + 0.5 * double(fp + fn);
+            return den == 0.0 ? nan : double(tp) / den;
+        }
+        case MET_MCC: {
+            const long long p_pred = tp + fp, n_pred = fn + tn, p_act = tp + fn, n_act = fp + tn;
+            if (p_pred == 0) return mcc_eps(double(tn), double(fn));
+            if (n_pred == 0) return mcc_eps(double(tp), double(fp));
+            if (p_act == 0) return mcc_eps(double(tn), double(fp));
+            if (n_act == 0) return mcc_eps(double(tp), double(fn));
+            const __int128 num = (__int128)tp * tn - (__int128)fp * fn;
+            // the reference multiplies the four Int64 counts (and overflows beyond ~3e18); here the
+            // product is formed in floating point
+            return double(num) / sqrt(double(p_pred) * double(n_pred) * double(p_act) * double(n_act));
+        }
+        case MET_ACC: {
+            const long long den = (tp + tn) + (fp + fn);
+            return den == 0 ? nan : double(tp + tn) / double(den);
+        }
+        case MET_BACC:
+            return (double(tp) / double(tp + fn) + double(tn) / double(tn + fp)) / 2.0;
+        case MET_RECALL:
+            return (tp + fn) == 0 ? nan : double(tp) / double(tp + fn);
+        default:
+            return (tp + fp) == 0 ? nan : double(tp) / double(tp + fp);
+    }
+}
+
+// one value per unique threshold (run start); PASS 0: sum / max / NaN flag / count, PASS 1: sum of
+// squared deviations from `mean`.  partial: [4][nblocks]
+template <int PASS>
+__global__ void __launch_bounds__(CV_TPB)
+    sweep_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ lab, int64_t M,
+                 const CurveState* __restrict__ block_state, const unsigned long long* __restrict__ totals, int metric,
+                 double mean, double* __restrict__ partial, int64_t nblocks) {
+    const int64_t base = int64_t(blockIdx.x) * CV_TILE + int64_t(threadIdx.x) * CV_ITEMS;
+    uint64_t k[CV_ITEMS + 1];
+    uint8_t l[CV_ITEMS];
+    k[0] = (base > 0 && base - 1 < M) ? keys[base - 1] : 0;
+#pragma unroll
+    for (int i = 0; i < CV_ITEMS; ++i) {
+        const int64_t idx = base + i;
+        k[i + 1] = (idx < M) ? keys[idx] : 0;
+        l[i] = (idx < M) ? lab[idx] : 0;
+    }
+    CurveState agg = cs_identity();
+#pragma unroll
+    for (int i = 0; i < CV_ITEMS; ++i) {
+        const int64_t idx = base + i;
+        if (idx < M) {
+            const bool is_start = (idx == 0) || (k[i + 1] != k[i]);
+            CurveState e = {(unsigned long long)l[i], is_start ? (long long)idx : -1ll, 0ull};
+            agg = cs_combine(agg, e);
+        }
+    }
+    CurveState total;
+    CurveState excl = cs_block_exclusive(agg, &total);
+    CurveState run = cs_combine(block_state[blockIdx.x], excl);
+    const long long P = (long long)totals[0], N = (long long)M - P;
+    double sum = 0.0, mx = -1.0 / 0.0, cnt = 0.0, nanflag = 0.0;
+#pragma unroll
+    for (int i = 0; i < CV_ITEMS; ++i) {
+        const int64_t idx = base + i;
+        if (idx < M) {
+            const bool is_start = (idx == 0) || (k[i + 1] != k[i]);
+            if (is_start) {  // threshold = this score: predicted positive <=> score >= threshold
+                const long long below_pos = (long long)run.pos, below_all = idx;
+                const long long fn = below_pos, tn = below_all - below_pos;
+                const double v = confusion_metric(metric, tn, N - tn, fn, P - fn);
+                if (PASS == 0) {
+                    if (v != v) nanflag = 1.0;
+                    else { sum += v; mx = fmax(mx, v); }
+                    cnt += 1.0;
+                } else {
+                    const double dlt = v - mean;
+                    sum += dlt * dlt;
+                }
+            }
+            CurveState e = {(unsigned long long)l[i], is_start ? (long long)idx : -1ll, 0ull};
+            run = cs_combine(run, e);
+        }
+    }
+    __shared__ double s0[CV_TPB], s1[CV_TPB], s2[CV_TPB], s3[CV_TPB];
+    s0[threadIdx.x] = sum;
+    s1[threadIdx.x] = mx;
+    s2[threadIdx.x] = cnt;
+    s3[threadIdx.x] = nanflag;
+    __syncthreads();
+    for (int st = CV_TPB / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            s0[threadIdx.x] += s0[threadIdx.x + st];
+            s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + st]);
+            s2[threadIdx.x] += s2[threadIdx.x + st];
+            s3[threadIdx.x] += s3[threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s0[0];
+        partial[nblocks + blockIdx.x] = s1[0];
+        partial[2 * nblocks + blockIdx.x] = s2[0];
+        partial[3 * nblocks + blockIdx.x] = s3[0];
+    }
+}
+
+// out[0] = sum, out[1] = max, out[2] = count, out[3] = NaN count
+__global__ void __launch_bounds__(1024)
+    sweep_final_kernel(const double* __restrict__ partial, int64_t nblocks, double* __restrict__ out) {
+    __shared__ double s0[1024], s1[1024], s2[1024], s3[1024];
+    const int t = threadIdx.x;
+    double a = 0.0, b = -1.0 / 0.0, c = 0.0, d = 0.0;
+    for (int64_t i = t; i < nblocks; i += 1024) {
+        a += partial[i];
+        b = fmax(b, partial[nblocks + i]);
+        c += partial[2 * nblocks + i];
+        d += partial[3 * nblocks + i];
+    }
+    s0[t] = a; s1[t] = b; s2[t] = c; s3[t] = d;
+    __syncthreads();
+    for (int st = 512; st > 0; st >>= 1) {
+        if (t < st) {
+            s0[t] += s0[t + st];
+            s1[t] = fmax(s1[t], s1[t + st]);
+            s2[t] += s2[t + st];
+            s3[t] += s3[t + st];
+        }
+        __syncthreads();
+    }
+    if (t == 0) { out[0] = s0[0]; out[1] = s1[0]; out[2] = s2[0]; out[3] = s3[0]; }
+}
+
+// BEDROC (reference src/performance.jl:22-38): sum over the positives of exp(-alpha * rank / N),
+// ranks 1-based in the stable descending order (= ascending order of the inverted keys).
+__global__ void __launch_bounds__(256)
+    bedroc_sum_kernel(const uint8_t* __restrict__ lab, int64_t M, double alpha, double* __restrict__ partial,
+                      unsigned long long* __restrict__ npos_partial) {
+    __shared__ double s[256];
+    __shared__ unsigned long long c[256];
+    double acc = 0.0;
+    unsigned long long n = 0;
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < M; i += int64_t(gridDim.x) * 256)
+        if (lab[i]) {
+            acc += exp(-alpha * double(i + 1) / double(M));
+            ++n;
+        }
+    s[threadIdx.x] = acc;
+    c[threadIdx.x] = n;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            s[threadIdx.x] += s[threadIdx.x + st];
+            c[threadIdx.x] += c[threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s[0];
+        npos_partial[blockIdx.x] = c[0];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    make_keys_mat_inv_kernel(const double* __restrict__ R, int64_t ldr, const double* __restrict__ Y, int64_t ldy,
+                             int64_t rows, int64_t cols, int invert, uint64_t* __restrict__ keys,
+                             uint8_t* __restrict__ lab) {
+    const int64_t r = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+        const uint64_t k = isless_key(R[c * ldr + r]);
+        keys[c * rows + r] = invert ? ~k : k;
+        lab[c * rows + r] = (Y[c * ldy + r] == 1.0) ? 1 : 0;  // BEDROC counts `y .== 1`
+    }
+}
+
+// stable ascending LSD radix sort of the (key, label) pairs; *kout / *lout point at the sorted arrays
+int32_t sort_pairs(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB, uint8_t* labB, int64_t M,
+                   uint64_t** kout_p, uint8_t** lout_p) {
     using namespace ss;
     void* p;
     const int64_t nblocks = ceil_div(M, RS_TILE);
-    // scratch: global digit histogram (8*256 u64) | per-pass hist (256*nblocks u32) | offsets (u64)
-    SS_TRY(scratch_get(ctx, 11, size_t(8 * 256) * 8 + size_t(256) * nblocks * 4 + size_t(256) * nblocks * 8 + 64, &p));
+    // scratch: global digit histogram (8*256 u64) | digit totals, digit bases (256 u64 each) |
+    // per-pass hist (256*nblocks u32) | per-(digit, block) relative offsets (u32)
+    SS_TRY(scratch_get(ctx, 11, size_t(8 * 256 + 512) * 8 + size_t(256) * nblocks * 4 * 2 + 64, &p));
     unsigned long long* ghist = static_cast<unsigned long long*>(p);
-    uint64_t* offsets = reinterpret_cast<uint64_t*>(ghist + 8 * 256);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(offsets + 256 * nblocks);
+    unsigned long long* dtotals = ghist + 8 * 256;
+    unsigned long long* dbase = dtotals + 256;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(dbase + 256);
+    uint32_t* rel = hist + 256 * nblocks;
+    const size_t ds_smem = size_t(RS_TILE) * 8 + (RS_TPB / 32) * 256 * 4 + 256 * 8 + 256 * 4 + 8 * 4 + RS_TILE;
+    SS_CHECK_CUDA(cudaFuncSetAttribute(rs_downsweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ds_smem)));
     SS_CHECK_CUDA(cudaMemsetAsync(ghist, 0, 8 * 256 * 8, ctx->stream));
     int hgrid = int(ceil_div(M, 256 * 64));
     if (hgrid > ctx->sm_count * 8) hgrid = ctx->sm_count * 8;
@@ -485,14 +839,27 @@ int32_t sort_and_integrate(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t
             if (hh[d * 256 + b] == (unsigned long long)M) trivial = true;
         if (trivial) continue;  // every key has the same digit: the pass is the identity
         rs_upsweep_kernel<<<unsigned(nblocks), RS_TPB, 0, ctx->stream>>>(kin, M, 8 * d, hist, nblocks);
-        rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nblocks, offsets);
-        rs_downsweep_kernel<<<unsigned(nblocks), RS_TPB, 0, ctx->stream>>>(kin, lin, M, 8 * d, offsets, nblocks, kout,
-                                                                            lout);
-        ctx->launches += 3;
+        rs_scan_rows_kernel<<<256, 1024, 0, ctx->stream>>>(hist, nblocks, rel, dtotals);
+        rs_scan_totals_kernel<<<1, 256, 0, ctx->stream>>>(dtotals, dbase);
+        rs_downsweep_kernel<<<unsigned(nblocks), RS_TPB, ds_smem, ctx->stream>>>(kin, lin, M, 8 * d, rel, dbase, nblocks,
+                                                                                  kout, lout);
+        ctx->launches += 4;
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint8_t* tl = lin; lin = lout; lout = tl;
     }
     SS_CHECK_CUDA(cudaGetLastError());
+    *kout_p = kin;
+    *lout_p = lin;
+    return SS_OK;
+}
+
+int32_t sort_and_integrate(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB, uint8_t* labB, int64_t M,
+                           double* out2) {
+    using namespace ss;
+    void* p;
+    uint64_t* kin;
+    uint8_t* lin;
+    SS_TRY(sort_pairs(ctx, keysA, labA, keysB, labB, M, &kin, &lin));
     // curve integration over (kin, lin)
     const int64_t cblocks = ceil_div(M, CV_TILE);
     SS_TRY(scratch_get(ctx, 12, size_t(cblocks) * sizeof(CurveState) + size_t(2 * cblocks) * 8 + 64, &p));
@@ -531,6 +898,15 @@ namespace ss {
 int32_t launch_topl(ss_ctx* ctx, const double* R, int64_t rows, int64_t cols, int64_t ld, int L, int32_t* idx_out,
                     double* val_out, int64_t ldv) {
     if (rows == 0) return SS_OK;
+    if (L <= 32) {
+        const size_t wsm = size_t(WT_ROWS) * (WT_COLS + 1) * 8;
+        SS_CHECK_CUDA(cudaFuncSetAttribute(topl_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsm)));
+        topl_warp_kernel<<<unsigned(ceil_div(rows, WT_ROWS)), WT_TPB, wsm, ctx->stream>>>(R, rows, cols, ld, L, idx_out,
+                                                                                         val_out, ldv);
+        SS_CHECK_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SS_OK;
+    }
     const size_t smem = size_t(L) * TOPL_TPB * (8 + 8 + 4);
     SS_REQUIRE(smem <= 200 * 1024, "top-L: L = %d is too large (max %d)", L, int(200 * 1024 / (TOPL_TPB * 20)));
     if (smem > 48 * 1024)
@@ -578,6 +954,108 @@ int32_t auroc_auprc(ss_ctx* ctx, const uint8_t* labels, const double* scores, in
     make_keys_kernel<<<grid, 256, 0, ctx->stream>>>(scores, labels, M, kA, lA);
     ctx->launches++;
     return sort_and_integrate(ctx, kA, lA, kB, lB, M, out2);
+}
+
+// max / mean / std (corrected) of a confusion-matrix metric over all unique thresholds
+int32_t threshold_sweep(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int metric, double* out4) {
+    const int64_t M = R->rows * R->cols;
+    const double nan = __builtin_nan("");
+    if (M == 0) {
+        out4[0] = out4[1] = out4[2] = nan;
+        out4[3] = 0;
+        return SS_OK;
+    }
+    uint64_t *kA, *kB, *kin;
+    uint8_t *lA, *lB, *lin;
+    SS_TRY(alloc_sort_buffers(ctx, M, &kA, &kB, &lA, &lB));
+    const int64_t gx = ceil_div(R->rows, 256);
+    int64_t gy = ceil_div(int64_t(ctx->sm_count) * 16, gx);
+    if (gy > R->cols) gy = R->cols;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    dim3 grid{unsigned(gx), unsigned(gy)};
+    make_keys_mat_kernel<<<grid, 256, 0, ctx->stream>>>(R->d, R->ld, Y->d, Y->ld, R->rows, R->cols, kA, lA);
+    ctx->launches++;
+    SS_TRY(sort_pairs(ctx, kA, lA, kB, lB, M, &kin, &lin));
+    const int64_t cblocks = ceil_div(M, CV_TILE);
+    void* p;
+    SS_TRY(scratch_get(ctx, 12, size_t(cblocks) * sizeof(CurveState) + size_t(4 * cblocks) * 8 + 128, &p));
+    CurveState* bstate = static_cast<CurveState*>(p);
+    double* partial = reinterpret_cast<double*>(bstate + cblocks);
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(partial + 4 * cblocks);
+    double* dout = reinterpret_cast<double*>(totals + 2);
+    curve_kernel<false><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, nullptr, nullptr, cblocks);
+    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(bstate, cblocks, totals);
+    sweep_kernel<0><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, totals, metric, 0.0, partial, cblocks);
+    sweep_final_kernel<<<1, 1024, 0, ctx->stream>>>(partial, cblocks, dout);
+    ctx->launches += 4;
+    double h[4];
+    SS_CHECK_CUDA(cudaMemcpyAsync(h, dout, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double n = h[2];
+    const bool has_nan = h[3] > 0;
+    const double mean = has_nan ? nan : h[0] / n;
+    out4[0] = has_nan ? nan : h[1];  // Julia's maximum / mean propagate NaN
+    out4[1] = mean;
+    out4[3] = n;
+    if (has_nan || n < 2) {
+        out4[2] = nan;
+        return SS_OK;
+    }
+    sweep_kernel<1><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, totals, metric, mean, partial, cblocks);
+    sweep_final_kernel<<<1, 1024, 0, ctx->stream>>>(partial, cblocks, dout);
+    ctx->launches += 2;
+    SS_CHECK_CUDA(cudaMemcpyAsync(h, dout, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    out4[2] = sqrt(h[0] / (n - 1.0));
+    return SS_OK;
+}
+
+int32_t bedroc(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int rev, double alpha, double* out) {
+    const int64_t M = R->rows * R->cols;
+    if (M == 0) {
+        *out = __builtin_nan("");
+        return SS_OK;
+    }
+    uint64_t *kA, *kB, *kin;
+    uint8_t *lA, *lB, *lin;
+    SS_TRY(alloc_sort_buffers(ctx, M, &kA, &kB, &lA, &lB));
+    const int64_t gx = ceil_div(R->rows, 256);
+    int64_t gy = ceil_div(int64_t(ctx->sm_count) * 16, gx);
+    if (gy > R->cols) gy = R->cols;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    dim3 grid{unsigned(gx), unsigned(gy)};
+    make_keys_mat_inv_kernel<<<grid, 256, 0, ctx->stream>>>(R->d, R->ld, Y->d, Y->ld, R->rows, R->cols, rev ? 1 : 0, kA, lA);
+    ctx->launches++;
+    if (M > 1) SS_TRY(sort_pairs(ctx, kA, lA, kB, lB, M, &kin, &lin));
+    else { kin = kA; lin = lA; }
+    int nb = int(ceil_div(M, 256 * 16));
+    if (nb > 1024) nb = 1024;
+    void* p;
+    SS_TRY(scratch_get(ctx, 12, size_t(nb) * 16 + 64, &p));
+    double* partial = static_cast<double*>(p);
+    unsigned long long* npart = reinterpret_cast<unsigned long long*>(partial + nb);
+    bedroc_sum_kernel<<<nb, 256, 0, ctx->stream>>>(lin, M, alpha, partial, npart);
+    ctx->launches++;
+    std::vector<double> hs(nb);
+    std::vector<unsigned long long> hn(nb);
+    SS_CHECK_CUDA(cudaMemcpyAsync(hs.data(), partial, size_t(nb) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaMemcpyAsync(hn.data(), npart, size_t(nb) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    double ssum = 0.0;
+    unsigned long long n = 0;
+    for (int i = 0; i < nb; ++i) {
+        ssum += hs[i];
+        n += hn[i];
+    }
+    // closed-form normalisation, reference src/performance.jl:32-37
+    const double Nn = double(M), Ra = double(n) / Nn;
+    const double rand_sum = Ra * (1.0 - exp(-alpha)) / (exp(alpha / Nn) - 1.0);
+    const double fac = Ra * sinh(alpha / 2.0) / (cosh(alpha / 2.0) - cosh(alpha / 2.0 - alpha * Ra));
+    const double cte = 1.0 / (1.0 - exp(alpha * (1.0 - Ra)));
+    *out = ssum * fac / rand_sum + cte;
+    return SS_OK;
 }
 
 int32_t auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, double* out2) {

@@ -802,3 +802,99 @@ def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: 
         rec["validity_ratio"] = float(kq.to_host().astype(np.int64).sum() / (len(qi) * nt))
         out.append(rec)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the rest of the metric family on the shared device sort, and `save`
+# ------------------------------------------------------------------------------------------------
+
+
+def BEDROC(y, yhat, rev: bool = True, alpha: float = 20.0) -> float:
+    """reference src/performance.jl:22-38 (positives are `y .== 1`, ranks from the stable
+    `sortperm(yhat; rev=rev)`)."""
+    ctx = Context.default()
+    y = np.asarray(y).ravel()
+    yhat = np.asarray(yhat, dtype=np.float64).ravel()
+    assert len(y) == len(yhat), "The number of scores must be equal to the number of labels"
+    dy = DMat.from_host(ctx, (y == 1).astype(np.float64).reshape(-1, 1))
+    ds = DMat.from_host(ctx, yhat.reshape(-1, 1))
+    out = C.c_double()
+    check(lib().ss_bedroc(ctx.h, dy.h, ds.h, int(bool(rev)), float(alpha), C.byref(out)))
+    return float(out.value)
+
+
+def _metric_id(metric) -> int:
+    table = {f1score: 0, mcc: 1, accuracy: 2, balancedaccuracy: 3, recall: 4, precision: 5}
+    if metric not in table:
+        raise TypeError("metric must be one of f1score, mcc, accuracy, balancedaccuracy, recall, precision")
+    return table[metric]
+
+
+def _sweep(y, yhat, metric):
+    ctx = Context.default()
+    y = np.asarray(y).ravel()
+    yhat = np.asarray(yhat, dtype=np.float64).ravel()
+    assert len(y) == len(yhat), "The number of scores must be equal to the number of labels"
+    dy = DMat.from_host(ctx, (y != 0).astype(np.float64).reshape(-1, 1))
+    ds = DMat.from_host(ctx, yhat.reshape(-1, 1))
+    out = (C.c_double * 4)()
+    check(lib().ss_threshold_sweep(ctx.h, dy.h, ds.h, _metric_id(metric), out))
+    return float(out[0]), float(out[1]), float(out[2])
+
+
+def maxperformance(y, yhat, metric) -> float:
+    """reference src/performance.jl:425-448: maximum of `metric` over the confusion matrices of all
+    unique-score thresholds."""
+    return _sweep(y, yhat, metric)[0]
+
+
+def meanperformance(y, yhat, metric) -> float:
+    """reference src/performance.jl:459-489."""
+    return _sweep(y, yhat, metric)[1]
+
+
+def meanstdperformance(y, yhat, metric) -> Tuple[float, float]:
+    """reference src/performance.jl:500-531 (`mean_and_std`, corrected sample std)."""
+    _, m, sd = _sweep(y, yhat, metric)
+    return m, sd
+
+
+def _jl_string(x) -> str:
+    """Julia `string(x)` for the numbers `save` writes (Int or Float64, shortest round-trip)."""
+    if isinstance(x, (bool, np.bool_)):
+        return "true" if x else "false"
+    if isinstance(x, (int, np.integer)):
+        return str(int(x))
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Inf" if x > 0 else "-Inf"
+    r = repr(x)
+    if "e" in r:
+        mant, exp = r.split("e")
+        if "." not in mant:
+            mant += ".0"
+        return f"{mant}e{int(exp)}"
+    return r
+
+
+def save(filepath: str, *args, delimiter: str = "\t") -> None:
+    """`save(filepath, yhat, y; delimiter)` (reference src/core.jl:503-522: the fold column is the
+    1-based index of the query) and `save(filepath, fidx, yhat, y; delimiter)` (:542-561).  Rows
+    `fold, "source", "target", score, label` are APPENDED ("a+"), as in the reference."""
+    if len(args) == 2:
+        fidx, (yhat, y) = None, args
+    elif len(args) == 3:
+        fidx, yhat, y = args
+    else:
+        raise TypeError("MethodError: no method matching save(...)")
+    queries, targets = y.names(1), y.names(2)
+    yh = yhat[queries, targets].array
+    yy = y.array
+    with open(filepath, "a+") as f:
+        for qi, q in enumerate(queries):
+            fold = (queries.index(q) + 1) if fidx is None else fidx
+            for ti, t in enumerate(targets):
+                row = [_jl_string(fold), '"' + q + '"', '"' + t + '"', _jl_string(yh[qi, ti]), _jl_string(yy[qi, ti])]
+                f.write(delimiter.join(row) + "\n")

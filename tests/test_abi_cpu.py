@@ -78,3 +78,17 @@ def test_host_bookkeeping_without_gpu():
     assert ss.recall(3, 2, 2, 3) == pytest.approx(0.6)
     assert ss.precision(3, 2, 2, 3) == pytest.approx(0.6)
     assert ss.mcc(0, 5, 0, 5) - ss.mcc(5, 5) < 1e-5
+
+
+def test_save_matches_reference_fixtures(tmp_path, kats):
+    """`save` is host-only I/O: byte-exact against test/data/save1..4 (test/runtests.jl:185-203)."""
+    sv = kats["save"]
+    y = ss.NamedArray(np.array(sv["y"]), (sv["rows"], sv["cols"]))
+    yhat = y.copy()
+    for name, args, kw in (("save1", (y, yhat), {}), ("save2", (y, yhat), {"delimiter": " "}),
+                           ("save3", (1, y, yhat), {}), ("save4", (1, y, yhat), {"delimiter": " "})):
+        p = tmp_path / name
+        ss.save(str(p), *args, **kw)
+        assert p.read_text() == sv["files"][name]
+    ss.save(str(tmp_path / "save1"), y, yhat)  # "a+": appends
+    assert (tmp_path / "save1").read_text() == sv["files"]["save1"] * 2

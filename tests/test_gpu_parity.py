@@ -643,3 +643,24 @@ def test_predict_tf32_mode_against_oracle(ss, o):
     assert np.array_equal(got.array[exact.array == 0], exact.array[exact.array == 0])
     with pytest.raises(ValueError):
         ss.predict((A, B), DT[q, tn], precision="f16")
+
+
+def test_bedroc_and_threshold_sweeps_against_oracle(ss, o):
+    rng = np.random.default_rng(8)
+    M = 20000
+    y = rng.random(M) < 0.05
+    s = np.round(rng.random(M) * (y * 0.4 + 0.6), 3)  # ties
+    s[rng.random(M) < 0.3] = 0.0
+    assert ss.BEDROC(y, s) == pytest.approx(o.BEDROC(y, s), rel=1e-12)
+    assert ss.BEDROC(y, s, rev=False, alpha=5.0) == pytest.approx(o.BEDROC(y, s, rev=False, alpha=5.0), rel=1e-12)
+    pairs = [(ss.f1score, o.f1score), (ss.mcc, o.mcc), (ss.accuracy, o.accuracy),
+             (ss.balancedaccuracy, o.balancedaccuracy), (ss.recall, o.recall), (ss.precision, o.precision)]
+    for mine, ref in pairs:
+        assert ss.maxperformance(y, s, mine) == pytest.approx(o.maxperformance(y, s, ref), rel=1e-12, nan_ok=True)
+        assert ss.meanperformance(y, s, mine) == pytest.approx(o.meanperformance(y, s, ref), rel=1e-11, nan_ok=True)
+        m, sd = ss.meanstdperformance(y, s, mine)
+        mo, sdo = o.meanstdperformance(y, s, ref)
+        assert m == pytest.approx(mo, rel=1e-11, nan_ok=True) and sd == pytest.approx(sdo, rel=1e-9, nan_ok=True)
+    # a metric that is NaN at some threshold poisons max / mean, as Julia's maximum / mean do
+    yn = np.zeros(50, bool)
+    assert math.isnan(ss.maxperformance(yn, rng.random(50), ss.recall))
