@@ -57,6 +57,11 @@ extern "C" {
  * tcgen05.mma kind::tf32, FP32 accumulation in TMEM; measured max relative error 2e-4 at K = 20000. */
 #define SS_PRECISION_F64 0u
 #define SS_PRECISION_TF32 (1u << 4)
+/* FP64-grade results from exact INT8 tensor-core products (Ozaki-style 8-bit slicing of non-negative
+ * operands, INT32 accumulation in TMEM, FP64 recombination; csrc/ss_umma.cu).  The error bound is
+ * normwise (~1e-13 of a typical entry with the default 6 slices at K = 20000), not element-wise,
+ * so the mode is opt-in; SS_INT8_SLICES=4..8 in the environment changes the slice count. */
+#define SS_PRECISION_F64_INT8 (3u << 4)
 #define SS_PRECISION_MASK (15u << 4)
 
 /* ss_gemm_f64 operand form of A */
@@ -149,7 +154,7 @@ SS_API int32_t ss_spread_rows(ss_ctx* ctx, const ss_mat* G, const ss_ivec* k, ss
 SS_API int32_t ss_gemm_f64(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
                     const ss_ivec* row_div, const ss_ivec* col_flag);
 /* Same contract as ss_gemm_f64 (FP64 operands in, FP64 C out) with the product computed by
- * tcgen05.mma kind::tf32 (accumulators in TMEM): precision = SS_PRECISION_TF32. */
+ * tcgen05.mma (accumulators in TMEM): precision = SS_PRECISION_TF32 or SS_PRECISION_F64_INT8. */
 SS_API int32_t ss_gemm_lowp(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss_mat* B, ss_mat* C,
                             const ss_ivec* row_div, const ss_ivec* col_flag, uint32_t precision);
 /* Fused GEMM + all-gather for the multi-GPU chain: as ss_gemm_f64, and every element of C is also

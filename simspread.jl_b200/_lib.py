@@ -16,7 +16,7 @@ P = C.POINTER
 SS_OK, SS_ERR_INVALID, SS_ERR_CUDA, SS_ERR_NO_DEVICE, SS_ERR_ASSERT, SS_ERR_OOM, SS_ERR_UNSUPPORTED = range(7)
 SS_PREDICT_CLEAN = 1
 SS_OP_N, SS_OP_T = 0, 1
-SS_PRECISION_F64, SS_PRECISION_TF32 = 0, 1 << 4
+SS_PRECISION_F64, SS_PRECISION_TF32, SS_PRECISION_F64_INT8 = 0, 1 << 4, 3 << 4
 
 
 class SimSpreadError(RuntimeError):

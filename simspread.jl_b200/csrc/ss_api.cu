@@ -492,6 +492,14 @@ static int32_t chain_gemm(ss_ctx* ctx, uint32_t precision, int opA, const double
         return launch_gemm_f64(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
     if (precision == SS_PRECISION_TF32)
         return launch_gemm_tf32(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
+    if (precision == SS_PRECISION_F64_INT8) {
+        int S = 6;
+        if (const char* env = getenv("SS_INT8_SLICES")) {
+            const int v = atoi(env);
+            if (v >= 2 && v <= 8) S = v;
+        }
+        return launch_gemm_i8(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, S);
+    }
     set_error("unknown precision flag 0x%x", precision);
     return SS_ERR_INVALID;
 }

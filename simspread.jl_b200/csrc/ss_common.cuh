@@ -111,6 +111,9 @@ int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, cons
 int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                          int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
                          bool split);
+int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                       int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
+                       int S);
 int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr* XsT, const ss_mat* Y, ss_mat* R, uint32_t flags,

@@ -18,9 +18,19 @@
 //                          epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 4-7 epilogue   : tcgen05.ld (32 lanes x 32 columns per instruction) -> FP64 -> fused
 //                          normalisation (/kf, clean! flag) -> column-major C
-// Operand pairs (A_p, B_p) are concatenated along K, which is how the 3xTF32 passes (and, later,
-// integer slices) share one accumulator.
+// Operand pairs (A_p, B_p) are concatenated along K inside one accumulator ("group"); a tile may run
+// several groups, each with its own TMEM accumulator pass and epilogue scale.
+//
+//   SS_PRECISION_F64_INT8 : FP64-grade products from INTEGER tensor-core math (Ozaki-style slicing).
+//   Each non-negative FP64 operand row is scaled by a power of two and cut into S unsigned 8-bit
+//   slices, x = 2^e * sum_i q_i 2^(-8i); slice products q_i^A * q_j^B are accumulated EXACTLY in
+//   INT32 by tcgen05.mma kind::i8 (groups are sized so that the unsigned 32-bit sum cannot wrap), and
+//   the epilogue adds 2^(ea+eb-8(i+j)) * G_ij into the FP64 result (every term exact, ~S roundings in
+//   the final sum).  Pairs with i+j > S+1 are dropped: the error is bounded by
+//   ~(S+1)*K*2^(-8S) * rowmax(A)*colmax(B) -- a NORMWISE bound (1e-13 of a typical entry for S = 6,
+//   K = 20000), not the element-wise 1e-12 of the default DMMA path, which is why this mode is opt-in.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ss_common.cuh"
 
@@ -32,26 +42,35 @@ constexpr int A_ST_BYTES = UM * 128;  // 16 KB
 constexpr int B_ST_BYTES = UN * 128;  // 32 KB
 constexpr int ST_BYTES = A_ST_BYTES + B_ST_BYTES;
 constexpr int U_THREADS = 256;
-constexpr int MAXP = 4;
+constexpr int MAXS = 8;    // operand slices (tensor maps) per side
+constexpr int MAXPAIR = 36; // slice pairs per tile
+constexpr int MAXGRP = 36;  // accumulator groups per tile
 constexpr int U_GROUP_M = 8;
+constexpr int U_SYNC_CHUNK = 32;  // 128-byte slabs between lockstep checkpoints
 constexpr size_t U_SMEM = size_t(U_STAGES) * ST_BYTES + 1024 + 256;
 
 struct UmmaMaps {
-    CUtensorMap a[MAXP];
-    CUtensorMap b[MAXP];
+    CUtensorMap a[MAXS];
+    CUtensorMap b[MAXS];
 };
 
 struct UmmaParams {
     int M, N;
-    int npairs;
     int kslabs;  // 128-byte K slabs per operand pair
     int bke;     // elements per slab
     int tiles_m, tiles_n;
     uint32_t idesc;
+    int ngroups;                 // accumulator passes per tile
+    int gstart[MAXGRP + 1];      // pairs [gstart[g], gstart[g+1]) share accumulator g
+    double gscale[MAXGRP];       // epilogue scale of group g (2^(-8(i+j)) for integer slices)
+    signed char pa[MAXPAIR], pb[MAXPAIR];  // slice index of A / B for every pair
     double* C;
     int64_t ldc;
     const int32_t* row_div;
     const int32_t* col_flag;
+    const double* rscale;  // integer mode: 2^ea[m]
+    const double* cscale;  // integer mode: 2^eb[n]
+    int* sync_prog;        // loose lockstep of the producers (see ss_gemm.cu), optional
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -97,15 +116,27 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
            (uint64_t(2) << 61);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+template <int KIND>  // 0: kind::tf32 (FP32 accumulate), 1: kind::i8 (INT32 accumulate)
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -137,8 +168,9 @@ __device__ __forceinline__ UTile utile(int tile, int tiles_m, int tiles_n) {
     return {first_m + r % gm, r / gm};
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(U_THREADS, 1)
-    ss_umma_tf32_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+    ss_umma_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ UmmaParams p) {
     extern __shared__ uint8_t usmem_raw[];
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem_base = (smem_u32(usmem_raw) + 1023u) & ~1023u;
@@ -176,22 +208,39 @@ __global__ void __launch_bounds__(U_THREADS, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int checkpoint = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const UTile tc = utile(tile, p.tiles_m, p.tiles_n);
                 const int m0 = tc.tm * UM, n0 = tc.tn * UN;
-                for (int pr = 0; pr < p.npairs; ++pr)
+                const int npairs = p.gstart[p.ngroups];
+                for (int pr = 0; pr < npairs; ++pr)
                     for (int kb = 0; kb < p.kslabs; ++kb) {
+                        if (p.sync_prog && (kb % U_SYNC_CHUNK) == 0) {
+                            // loose lockstep (same scheme and rationale as ss_gemm.cu): concurrent tiles
+                            // share operand panels through L2 only while they stream K at nearby positions
+                            ++checkpoint;
+                            *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = checkpoint;
+                            const long long t0 = clock64();
+                            for (;;) {
+                                int mn = 0x7fffffff;
+                                for (int i = 0; i < int(gridDim.x); ++i)
+                                    mn = min(mn, *reinterpret_cast<volatile int*>(p.sync_prog + i));
+                                if (mn >= checkpoint - 1 || clock64() - t0 > 400000ll) break;
+                                __nanosleep(256);
+                            }
+                        }
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * stage, ST_BYTES);
                         const uint32_t sA = smem_base + stage * ST_BYTES;
-                        tma_load_2d(sA, &maps.a[pr], kb * p.bke, m0, bar_full + 8 * stage);
-                        tma_load_2d(sA + A_ST_BYTES, &maps.b[pr], kb * p.bke, n0, bar_full + 8 * stage);
+                        tma_load_2d(sA, &maps.a[p.pa[pr]], kb * p.bke, m0, bar_full + 8 * stage);
+                        tma_load_2d(sA + A_ST_BYTES, &maps.b[p.pb[pr]], kb * p.bke, n0, bar_full + 8 * stage);
                         if (++stage == U_STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
             }
+            if (p.sync_prog) *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = 0x7fffffff;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -199,14 +248,15 @@ __global__ void __launch_bounds__(U_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+              for (int g = 0; g < p.ngroups; ++g, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * UN;
                 uint32_t accumulate = 0;
-                const int nslab = p.npairs * p.kslabs;
+                const int nslab = (p.gstart[g + 1] - p.gstart[g]) * p.kslabs;
                 for (int s = 0; s < nslab; ++s) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -215,7 +265,7 @@ __global__ void __launch_bounds__(U_THREADS, 1)
                     const uint64_t bdesc = make_kmajor_desc(sA + A_ST_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte slab
-                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accumulate);
+                        umma<KIND>(tmem_d, adesc + 2 * k, bdesc + 2 * k, p.idesc, accumulate);
                         accumulate = 1;
                     }
                     umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
@@ -231,42 +281,59 @@ __global__ void __launch_bounds__(U_THREADS, 1)
         // ================= epilogue =================
         const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const UTile tc = utile(tile, p.tiles_m, p.tiles_n);
             const int m0 = tc.tm * UM, n0 = tc.tn * UN;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(bar_tfull + 8 * as, aphase);
-            tc_fence_after();
             const int row = m0 + 32 * ew + lane;
-            const uint32_t taddr = tmem_base + (uint32_t(32 * ew) << 16) + as * UN;
-            double inv = 1.0;
+            double inv = 1.0, rs = 1.0;
             bool zero_row = false;
-            if (p.row_div && row < p.M) {
-                const int d = __ldg(p.row_div + row);
-                zero_row = (d == 0);
-                inv = double(d);
+            if (row < p.M) {
+                if (p.row_div) {
+                    const int d = __ldg(p.row_div + row);
+                    zero_row = (d == 0);
+                    inv = double(d);
+                }
+                if (KIND == 1) rs = __ldg(p.rscale + row);
             }
+            for (int g = 0; g < p.ngroups; ++g, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tfull + 8 * as, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t(32 * ew) << 16) + as * UN;
+                const bool first = (g == 0), last = (g == p.ngroups - 1);
+                const double gs = (KIND == 1) ? rs * p.gscale[g] : 1.0;
 #pragma unroll 1
-            for (int c = 0; c < UN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                if (row < p.M) {
+                for (int c = 0; c < UN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    if (row < p.M) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = n0 + c * 32 + j;
-                        if (col < p.N) {
-                            double v = double(__uint_as_float(r[j]));
-                            if (p.row_div) v = zero_row ? 0.0 : v / inv;
-                            if (p.col_flag && __ldg(p.col_flag + col) == 0) v = -99.0;
-                            p.C[int64_t(col) * p.ldc + row] = v;
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = n0 + c * 32 + j;
+                            if (col < p.N) {
+                                double* dst = p.C + int64_t(col) * p.ldc + row;
+                                double v;
+                                if (KIND == 0) {
+                                    v = double(__uint_as_float(r[j]));
+                                } else {
+                                    // exact: (uint32 < 2^32) * 2^k; the running FP64 sum lives in C (L2-hot)
+                                    v = double(r[j]) * (gs * __ldg(p.cscale + col));
+                                    if (!first) v += *dst;
+                                }
+                                if (last) {
+                                    if (p.row_div) v = zero_row ? 0.0 : v / inv;
+                                    if (p.col_flag && __ldg(p.col_flag + col) == 0) v = -99.0;
+                                }
+                                *dst = v;
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
         }
     }
     tc_fence_before();
@@ -340,24 +407,159 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// K-major FP32 operand: rows x K floats, row pitch kp floats; box = 32 floats (128 B) x box_rows
-int32_t make_map_f32(CUtensorMap* map, const float* base, int64_t K, int64_t rows, int64_t kp, int box_rows) {
+// K-major operand: `rows` x K elements of `esize` bytes, row pitch `pitch_bytes`; box = 128 B of K x box_rows
+int32_t make_map_kmajor(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize, int64_t K, int64_t rows,
+                        int64_t pitch_bytes, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         ss::set_error("cuTensorMapEncodeTiled is not available from the driver");
         return SS_ERR_CUDA;
     }
     cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(rows)};
-    cuuint64_t gstride[1] = {cuuint64_t(kp) * 4};
-    cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
+    cuuint64_t gstride[1] = {cuuint64_t(pitch_bytes)};
+    cuuint32_t box[2] = {cuuint32_t(128 / esize), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        ss::set_error("cuTensorMapEncodeTiled (f32) failed with CUresult %d", int(r));
+        ss::set_error("cuTensorMapEncodeTiled (k-major, %d-byte elements) failed with CUresult %d", esize, int(r));
         return SS_ERR_CUDA;
     }
+    return SS_OK;
+}
+
+// ---- FP64 -> unsigned 8-bit slices (integer mode) -----------------------------------------------
+// per-row scale 2^e with max|x| < 2^e, and flags: bit0 = negative entry, bit1 = NaN / Inf entry
+__device__ __forceinline__ double pow2_above(double mx) {
+    if (mx == 0.0) return 1.0;
+    int e;
+    frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+    return ldexp(1.0, e);
+}
+
+// k-contiguous source: element (k, j) at src[j*ld + k]; one block per row j
+__global__ void __launch_bounds__(256)
+    rowscale_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, double* __restrict__ scale,
+                           int* __restrict__ flags) {
+    __shared__ double smx[256];
+    for (int64_t j = blockIdx.x; j < J; j += gridDim.x) {
+        double mx = 0.0;
+        int bad = 0;
+        for (int64_t k = threadIdx.x; k < K; k += 256) {
+            const double x = src[j * ld + k];
+            if (x < 0.0) bad |= 1;
+            if (!(fabs(x) <= 1.7976931348623157e308)) bad |= 2;
+            mx = fmax(mx, fabs(x));
+        }
+        if (bad) atomicOr(flags, bad);
+        smx[threadIdx.x] = mx;
+        __syncthreads();
+        for (int st = 128; st > 0; st >>= 1) {
+            if (threadIdx.x < st) smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + st]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) scale[j] = pow2_above(smx[0]);
+        __syncthreads();
+    }
+}
+
+// m-contiguous source: element (m, k) at src[k*ld + m]; one thread per row m (coalesced over m)
+__global__ void __launch_bounds__(256)
+    rowscale_mmajor_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, double* __restrict__ scale,
+                           int* __restrict__ flags) {
+    const int64_t m = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (m >= M) return;
+    double mx = 0.0;
+    int bad = 0;
+    for (int64_t k = 0; k < K; ++k) {
+        const double x = __ldg(src + k * ld + m);
+        if (x < 0.0) bad |= 1;
+        if (!(fabs(x) <= 1.7976931348623157e308)) bad |= 2;
+        mx = fmax(mx, fabs(x));
+    }
+    if (bad) atomicOr(flags, bad);
+    scale[m] = pow2_above(mx);
+}
+
+// r in [0,1) -> S unsigned 8-bit digits, most significant first (all operations exact)
+template <int DUMMY = 0>
+__device__ __forceinline__ void slice_digits(double r, int S, uint8_t* out, int64_t plane) {
+    for (int i = 0; i < S; ++i) {
+        r *= 256.0;
+        const double q = floor(r);
+        r -= q;
+        out[int64_t(i) * plane] = uint8_t(int(q));
+    }
+}
+
+// k-contiguous source -> planes[i][j*kp + k]
+__global__ void __launch_bounds__(256)
+    slice_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, const double* __restrict__ scale,
+                        int S, uint8_t* __restrict__ planes, int64_t kp) {
+    const int64_t k = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (k >= kp) return;
+    const int64_t plane = J * kp;
+    for (int64_t j = blockIdx.y; j < J; j += gridDim.y) {
+        const double x = (k < K) ? src[j * ld + k] : 0.0;
+        slice_digits(fabs(x) / scale[j], S, planes + j * kp + k, plane);  // scale is a power of two: exact
+    }
+}
+
+// m-contiguous source -> planes[i][m*kp + k] (32x32 transpose through shared memory)
+__global__ void __launch_bounds__(256)
+    slice_mmajor_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, const double* __restrict__ scale,
+                        int S, uint8_t* __restrict__ planes, int64_t kp) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t m0 = int64_t(blockIdx.x) * 32, k0 = int64_t(blockIdx.y) * 32;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t m = m0 + tx, k = k0 + j;
+        tile[j][tx] = (m < M && k < K) ? src[k * ld + m] : 0.0;
+    }
+    __syncthreads();
+    const int64_t plane = M * kp;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t m = m0 + j, k = k0 + tx;
+        if (m < M && k < kp) slice_digits(fabs(tile[tx][j]) / scale[m], S, planes + m * kp + k, plane);
+    }
+}
+
+inline unsigned grid_y_for(const ss_ctx* ctx, int64_t gx, int64_t n) {
+    int64_t want = ss::ceil_div(int64_t(ctx->sm_count) * 16, gx);
+    if (want < 1) want = 1;
+    if (want > n) want = n;
+    if (want > 65535) want = 65535;
+    return unsigned(want);
+}
+
+template <int KIND>
+int32_t launch_umma(ss_ctx* ctx, const UmmaMaps& maps, UmmaParams q, double flops) {
+    const int64_t total = int64_t(q.tiles_m) * q.tiles_n;
+    const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);
+    q.sync_prog = nullptr;
+    // measured at C4: the lockstep turns the 21-pair integer kernel from HBM/power-bound (0.83 GHz,
+    // 3.55 s) into 1.70 GHz / 2.16 s; the short single-pass TF32 tiles lose 15 % to it, so it stays off
+    if (KIND == 1 && total > grid && !getenv("SS_NO_LOCKSTEP")) {
+        if (!ctx->tile_counter) SS_CHECK_CUDA(cudaMalloc(&ctx->tile_counter, 4096));
+        SS_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, size_t(grid) * 4, ctx->stream));
+        q.sync_prog = ctx->tile_counter;
+    }
+    SS_CHECK_CUDA(cudaFuncSetAttribute(ss_umma_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(U_SMEM)));
+    ss_ctx::ProfRec rec{nullptr, nullptr, flops};
+    if (ctx->profile) {
+        SS_CHECK_CUDA(cudaEventCreate(&rec.start));
+        SS_CHECK_CUDA(cudaEventCreate(&rec.stop));
+        SS_CHECK_CUDA(cudaEventRecord(rec.start, ctx->stream));
+    }
+    ss_umma_kernel<KIND><<<grid, U_THREADS, U_SMEM, ctx->stream>>>(maps, q);
+    SS_CHECK_CUDA(cudaGetLastError());
+    if (ctx->profile) {
+        SS_CHECK_CUDA(cudaEventRecord(rec.stop, ctx->stream));
+        ctx->prof.push_back(rec);
+    }
+    ctx->launches++;
     return SS_OK;
 }
 
@@ -365,56 +567,40 @@ int32_t make_map_f32(CUtensorMap* map, const float* base, int64_t K, int64_t row
 
 namespace ss {
 
-// C (FP64, column-major, M x N) = op(A) * B in TF32 (split == false) or 3xTF32 (split == true).
-// opA / operand layouts as launch_gemm_f64.  Scratch slots 14 (A) and 15 (B) hold the converted operands.
+// C (FP64, column-major, M x N) = op(A) * B with TF32 operands / FP32 accumulation on tcgen05.
+// Scratch slots 14 (A) and 15 (B) hold the converted operands.
 int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                          int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
-                         bool split) {
+                         bool /*split*/) {
     SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tf32: empty problem");
     SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_tf32: dimension too large");
     const int64_t kp = round_up(K, 32);
-    const int nbuf = split ? 2 : 1;
     void* p;
-    SS_TRY(scratch_get(ctx, 14, size_t(M) * kp * 4 * nbuf, &p));
+    SS_TRY(scratch_get(ctx, 14, size_t(M) * kp * 4, &p));
     float* Ahi = static_cast<float*>(p);
-    float* Alo = split ? Ahi + M * kp : nullptr;
-    SS_TRY(scratch_get(ctx, 15, size_t(N) * kp * 4 * nbuf, &p));
+    SS_TRY(scratch_get(ctx, 15, size_t(N) * kp * 4, &p));
     float* Bhi = static_cast<float*>(p);
-    float* Blo = split ? Bhi + N * kp : nullptr;
-    auto gy = [&](int64_t gx, int64_t n) {
-        int64_t want = ceil_div(int64_t(ctx->sm_count) * 16, gx);
-        if (want < 1) want = 1;
-        if (want > n) want = n;
-        if (want > 65535) want = 65535;
-        return unsigned(want);
-    };
     if (opA == SS_OP_N) {
         dim3 g{unsigned(ceil_div(M, 32)), unsigned(ceil_div(kp, 32))};
         SS_REQUIRE(g.y <= 65535, "gemm_tf32: K too large for the transpose grid");
-        cvt_transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, Ahi, Alo, kp);
+        cvt_transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, Ahi, nullptr, kp);
     } else {
         const int64_t gx = ceil_div(kp, 256);
-        dim3 g{unsigned(gx), gy(gx, M)};
-        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, Ahi, Alo, kp);
+        dim3 g{unsigned(gx), grid_y_for(ctx, gx, M)};
+        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, Ahi, nullptr, kp);
     }
     {
         const int64_t gx = ceil_div(kp, 256);
-        dim3 g{unsigned(gx), gy(gx, N)};
-        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, Bhi, Blo, kp);
+        dim3 g{unsigned(gx), grid_y_for(ctx, gx, N)};
+        cvt_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, Bhi, nullptr, kp);
     }
     ctx->launches += 2;
     SS_CHECK_CUDA(cudaGetLastError());
-
     UmmaMaps maps;
     UmmaParams q{};
-    q.npairs = split ? 3 : 1;
-    const float* ap[3] = {Ahi, Ahi, Alo};  // hi*hi, hi*lo, lo*hi
-    const float* bp[3] = {Bhi, Blo, Bhi};
-    for (int i = 0; i < q.npairs; ++i) {
-        SS_TRY(make_map_f32(&maps.a[i], ap[i], K, M, kp, UM));
-        SS_TRY(make_map_f32(&maps.b[i], bp[i], K, N, kp, UN));
-    }
-    for (int i = q.npairs; i < MAXP; ++i) {
+    SS_TRY(make_map_kmajor(&maps.a[0], Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, K, M, kp * 4, UM));
+    SS_TRY(make_map_kmajor(&maps.b[0], Bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, K, N, kp * 4, UN));
+    for (int i = 1; i < MAXS; ++i) {
         maps.a[i] = maps.a[0];
         maps.b[i] = maps.b[0];
     }
@@ -427,27 +613,114 @@ int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, con
     // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2) [10,13) |
     // a_major K (0) [15] | b_major K (0) [16] | N>>3 [17,23) | M>>4 [24,29)
     q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(UN >> 3) << 17) | (uint32_t(UM >> 4) << 24);
+    q.ngroups = 1;
+    q.gstart[0] = 0;
+    q.gstart[1] = 1;
+    q.gscale[0] = 1.0;
+    q.pa[0] = q.pb[0] = 0;
     q.C = C;
     q.ldc = ldc;
     q.row_div = row_div;
     q.col_flag = col_flag;
-    const int64_t total = int64_t(q.tiles_m) * q.tiles_n;
-    const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);
-    SS_CHECK_CUDA(cudaFuncSetAttribute(ss_umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(U_SMEM)));
-    ss_ctx::ProfRec rec{nullptr, nullptr, 2.0 * double(M) * double(N) * double(K)};
-    if (ctx->profile) {
-        SS_CHECK_CUDA(cudaEventCreate(&rec.start));
-        SS_CHECK_CUDA(cudaEventCreate(&rec.stop));
-        SS_CHECK_CUDA(cudaEventRecord(rec.start, ctx->stream));
+    return launch_umma<0>(ctx, maps, q, 2.0 * double(M) * double(N) * double(K));
+}
+
+// C = op(A) * B for NON-NEGATIVE FP64 operands from exact integer slice products (see file header).
+// S = number of 8-bit slices per operand (4..8).
+int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                       int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
+                       int S) {
+    SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8: empty problem");
+    SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_i8: dimension too large");
+    SS_REQUIRE(S >= 2 && S <= MAXS, "gemm_i8: 2..%d slices", MAXS);
+    const int64_t kp = round_up(K, 128);
+    // unsigned 32-bit accumulation of `g` pairs stays exact while g * K * 255^2 < 2^32
+    const int64_t per_group = int64_t(4294967295.0 / (double(kp) * 65025.0));
+    SS_REQUIRE(per_group >= 1, "gemm_i8: K = %lld is too long for exact INT32 accumulation (max 66048)", (long long)K);
+    void* p;
+    SS_TRY(scratch_get(ctx, 14, size_t(S) * M * kp + size_t(M) * 8 + 64, &p));
+    uint8_t* Ap = static_cast<uint8_t*>(p);
+    double* rs = reinterpret_cast<double*>(Ap + size_t(S) * M * kp);
+    SS_TRY(scratch_get(ctx, 15, size_t(S) * N * kp + size_t(N) * 8 + 64, &p));
+    uint8_t* Bp = static_cast<uint8_t*>(p);
+    double* cs = reinterpret_cast<double*>(Bp + size_t(S) * N * kp);
+    int* flags = reinterpret_cast<int*>(cs + N);
+    SS_CHECK_CUDA(cudaMemsetAsync(flags, 0, 4, ctx->stream));
+    const int rgrid = ctx->sm_count * 8;
+    if (opA == SS_OP_N) {
+        rowscale_mmajor_kernel<<<unsigned(ceil_div(M, 256)), 256, 0, ctx->stream>>>(A, M, K, lda, rs, flags);
+        dim3 g{unsigned(ceil_div(M, 32)), unsigned(ceil_div(kp, 32))};
+        SS_REQUIRE(g.y <= 65535, "gemm_i8: K too large for the transpose grid");
+        slice_mmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, rs, S, Ap, kp);
+    } else {
+        rowscale_kmajor_kernel<<<unsigned(M < rgrid ? M : rgrid), 256, 0, ctx->stream>>>(A, K, M, lda, rs, flags);
+        const int64_t gx = ceil_div(kp, 256);
+        dim3 g{unsigned(gx), grid_y_for(ctx, gx, M)};
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, rs, S, Ap, kp);
     }
-    ss_umma_tf32_kernel<<<grid, U_THREADS, U_SMEM, ctx->stream>>>(maps, q);
+    {
+        rowscale_kmajor_kernel<<<unsigned(N < rgrid ? N : rgrid), 256, 0, ctx->stream>>>(B, K, N, ldb, cs, flags);
+        const int64_t gx = ceil_div(kp, 256);
+        dim3 g{unsigned(gx), grid_y_for(ctx, gx, N)};
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, cs, S, Bp, kp);
+    }
+    ctx->launches += 4;
     SS_CHECK_CUDA(cudaGetLastError());
-    if (ctx->profile) {
-        SS_CHECK_CUDA(cudaEventRecord(rec.stop, ctx->stream));
-        ctx->prof.push_back(rec);
+    int hflags = 0;
+    SS_CHECK_CUDA(cudaMemcpyAsync(&hflags, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hflags) {
+        set_error("the int8-sliced precision mode needs finite, non-negative operands (%s entry found); "
+                  "use the default FP64 mode", (hflags & 2) ? "NaN/Inf" : "negative");
+        return SS_ERR_UNSUPPORTED;
     }
-    ctx->launches++;
-    return SS_OK;
+    UmmaMaps maps;
+    UmmaParams q{};
+    for (int i = 0; i < MAXS; ++i) {
+        const int s = i < S ? i : 0;
+        SS_TRY(make_map_kmajor(&maps.a[i], Ap + size_t(s) * M * kp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kp, M, kp, UM));
+        SS_TRY(make_map_kmajor(&maps.b[i], Bp + size_t(s) * N * kp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kp, N, kp, UN));
+    }
+    q.M = int(M);
+    q.N = int(N);
+    q.kslabs = int(kp / 128);
+    q.bke = 128;
+    q.tiles_m = int(ceil_div(M, UM));
+    q.tiles_n = int(ceil_div(N, UN));
+    // c_format S32 (2) | a_format / b_format unsigned 8-bit (0) | K-major | N>>3 | M>>4
+    q.idesc = (2u << 4) | (uint32_t(UN >> 3) << 17) | (uint32_t(UM >> 4) << 24);
+    // slice i (1-based weight 2^(-8i)) x slice j: keep i + j <= S + 1; smallest terms first
+    int np = 0, ng = 0;
+    q.gstart[0] = 0;
+    for (int d = S + 1; d >= 2; --d) {
+        int in_group = 0;
+        for (int i = 1; i <= S; ++i) {
+            const int j = d - i;
+            if (j < 1 || j > S) continue;
+            if (in_group == per_group) {
+                q.gscale[ng] = ldexp(1.0, -8 * d);
+                q.gstart[++ng] = np;
+                in_group = 0;
+            }
+            q.pa[np] = (signed char)(i - 1);
+            q.pb[np] = (signed char)(j - 1);
+            ++np;
+            ++in_group;
+        }
+        if (in_group) {
+            q.gscale[ng] = ldexp(1.0, -8 * d);
+            q.gstart[++ng] = np;
+        }
+    }
+    SS_REQUIRE(np <= MAXPAIR && ng <= MAXGRP, "gemm_i8: too many slice pairs");
+    q.ngroups = ng;
+    q.C = C;
+    q.ldc = ldc;
+    q.row_div = row_div;
+    q.col_flag = col_flag;
+    q.rscale = rs;
+    q.cscale = cs;
+    return launch_umma<1>(ctx, maps, q, 2.0 * double(M) * double(N) * double(K));
 }
 
 }  // namespace ss

@@ -453,7 +453,8 @@ def _dense_predict(A: NamedArray, B: NamedArray, rows, cols) -> NamedArray:
     return Fn[list(rows), list(cols)]
 
 
-_PRECISION_FLAGS = {"f64": _lib.SS_PRECISION_F64, "tf32": _lib.SS_PRECISION_TF32}
+_PRECISION_FLAGS = {"f64": _lib.SS_PRECISION_F64, "tf32": _lib.SS_PRECISION_TF32,
+                    "f64_int8": _lib.SS_PRECISION_F64_INT8}
 
 
 def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
@@ -470,7 +471,7 @@ def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
     if layout not in ("auto", "dense", "sparse"):
         raise ValueError("layout must be 'auto', 'dense' or 'sparse'")
     if precision not in _PRECISION_FLAGS:
-        raise ValueError("precision must be 'f64' (default) or 'tf32' (tcgen05, opt-in)")
+        raise ValueError("precision must be 'f64' (default), 'f64_int8' or 'tf32' (tcgen05, opt-in)")
     ctx = Context.default()
     if len(args) == 2 and isinstance(args[0], tuple):
         (A, B), yq = args

@@ -15,7 +15,8 @@ using NamedArrays
 using Random
 
 export cutoff, cutoff!, featurize, featurize!, k, construct, spread, predict, clean!,
-    AuROC, AuPRC, recallatL, precisionatL, validity_ratio
+    AuROC, AuPRC, BEDROC, recallatL, precisionatL, validity_ratio,
+    maxperformance, meanperformance, meanstdperformance
 
 const libss = get(ENV, "SIMSPREAD_B200_LIB",
     joinpath(@__DIR__, "..", "lib", "libsimspread_b200.so"))
@@ -23,6 +24,7 @@ const libss = get(ENV, "SIMSPREAD_B200_LIB",
 const SS_OP_N = Cint(0)
 const SS_OP_T = Cint(1)
 const SS_PREDICT_CLEAN = Cuint(1)
+const SS_PRECISION = Dict(:f64 => Cuint(0), :tf32 => Cuint(1 << 4), :f64_int8 => Cuint(3 << 4))
 const SS_ERR_ASSERT = Cint(4)
 
 # ---------------------------------------------------------------------------------------------
@@ -226,8 +228,8 @@ function spread(G::NamedMatrix)
     return W
 end
 
-function _predict_rows(g::Graph, rows, cols; clean::Bool=false)
-    flags = clean ? SS_PREDICT_CLEAN : Cuint(0)
+function _predict_rows(g::Graph, rows, cols; clean::Bool=false, precision::Symbol=:f64)
+    flags = (clean ? SS_PREDICT_CLEAN : Cuint(0)) | SS_PRECISION[precision]
     qpos = Dict(n => i for (i, n) in enumerate(g.queries))
     spos = Dict(n => i for (i, n) in enumerate(g.sources))
     tpos = Dict(n => i for (i, n) in enumerate(g.targets))
@@ -257,14 +259,15 @@ function _predict_rows(g::Graph, rows, cols; clean::Bool=false)
 end
 
 # `GPU` is accepted for signature compatibility; the computation always runs on the GPU in Float64
-function predict(I::Tuple{Graph,Graph}, ytest::NamedMatrix; GPU::Bool=false, clean::Bool=false)
+function predict(I::Tuple{Graph,Graph}, ytest::NamedMatrix; GPU::Bool=false, clean::Bool=false,
+    precision::Symbol=:f64)
     A, _ = I
-    return _predict_rows(A, names(ytest, 1), names(ytest, 2); clean=clean)
+    return _predict_rows(A, names(ytest, 1), names(ytest, 2); clean=clean, precision=precision)
 end
-predict(A::Graph, B::Graph, ytest::NamedMatrix; GPU::Bool=false, clean::Bool=false) =
-    predict((A, B), ytest; GPU=GPU, clean=clean)
-predict(A::Graph, ytrain::NamedMatrix; GPU::Bool=false, clean::Bool=false) =
-    _predict_rows(A, names(ytrain, 1), names(ytrain, 2); clean=clean)
+predict(A::Graph, B::Graph, ytest::NamedMatrix; GPU::Bool=false, clean::Bool=false, precision::Symbol=:f64) =
+    predict((A, B), ytest; GPU=GPU, clean=clean, precision=precision)
+predict(A::Graph, ytrain::NamedMatrix; GPU::Bool=false, clean::Bool=false, precision::Symbol=:f64) =
+    _predict_rows(A, names(ytrain, 1), names(ytrain, 2); clean=clean, precision=precision)
 
 # literal path for arbitrary dense (A, B) NamedArrays: F = A * (W * W), W = spread(B), on the GPU
 function predict(I::Tuple{T,T}, ytest::T; GPU::Bool=false) where {T<:NamedMatrix}
@@ -358,5 +361,29 @@ recallatL(y, yhat, grouping, L::Integer=20) = _atl_grouped(1, y, yhat, grouping,
 precisionatL(y, yhat, grouping, L::Integer=20) = _atl_grouped(2, y, yhat, grouping, L)
 
 validity_ratio(yhat::AbstractVector) = k(yhat) / length(yhat)
+
+function BEDROC(y::AbstractVector{Bool}, yhat::AbstractVector; rev::Bool=true, α::AbstractFloat=20.0)
+    @assert length(y) == length(yhat) "The number of scores must be equal to the number of labels"
+    dy, ds = DMat(reshape(Float64.(y .== 1), :, 1)), DMat(reshape(Float64.(yhat), :, 1))
+    out = Ref{Float64}(0.0)
+    check(ccall((:ss_bedroc, libss), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Float64, Ptr{Float64}),
+        ctx().h, dy.h, ds.h, rev, Float64(α), out))
+    return out[]
+end
+
+# metric is one of this module's f1score / mcc / accuracy / balancedaccuracy / recall / precision,
+# passed by name: ids follow include/simspread_b200.h
+const _METRIC_ID = Dict(:f1score => 0, :mcc => 1, :accuracy => 2, :balancedaccuracy => 3, :recall => 4, :precision => 5)
+function _sweep(y::AbstractVector, yhat::AbstractVector, metric::Function)
+    @assert length(y) == length(yhat) "The number of scores must be equal to the number of labels"
+    dy, ds = DMat(reshape(Float64.(y .!= 0), :, 1)), DMat(reshape(Float64.(yhat), :, 1))
+    out = zeros(Float64, 4)
+    GC.@preserve out check(ccall((:ss_threshold_sweep, libss), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}), ctx().h, dy.h, ds.h, _METRIC_ID[nameof(metric)], out))
+    return out
+end
+maxperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = _sweep(y, yhat, metric)[1]
+meanperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = _sweep(y, yhat, metric)[2]
+meanstdperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = (o = _sweep(y, yhat, metric); (o[2], o[3]))
 
 end # module

@@ -664,3 +664,61 @@ def test_bedroc_and_threshold_sweeps_against_oracle(ss, o):
     # a metric that is NaN at some threshold poisons max / mean, as Julia's maximum / mean do
     yn = np.zeros(50, bool)
     assert math.isnan(ss.maxperformance(yn, rng.random(50), ss.recall))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (129, 257, 133), (300, 520, 2600), (64, 200, 20000)])
+@pytest.mark.parametrize("op", ["N", "T"])
+def test_gemm_f64_from_int8_slices(ss, M, N, K, op):
+    """Opt-in FP64-grade mode on the INT8 tensor pipe: exact integer slice products, FP64
+    recombination.  Exact on integer operands; within the FP64 score tolerance on real data."""
+    from simspread_b200._lib import SS_OP_N, SS_OP_T, SS_PRECISION_F64_INT8, check
+    rng = np.random.default_rng(M + 3 * N + 7 * K)
+    ctx = ss.Context.default()
+    o_ = SS_OP_N if op == "N" else SS_OP_T
+    A = rng.integers(0, 250, size=(M, K)).astype(float)
+    B = rng.integers(0, 250, size=(K, N)).astype(float)
+    if M > 1:
+        A[0, :] = 0.0  # an all-zero row (scale 2^0, all digits 0)
+    dA, dB, dC = ss.DMat.from_host(ctx, A if op == "N" else A.T), ss.DMat.from_host(ctx, B), ss.DMat(ctx, M, N)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, None, None, SS_PRECISION_F64_INT8))
+    assert np.array_equal(dC.to_host(), A @ B)
+    # rows / columns of very different magnitude: the per-row power-of-two scaling keeps them exact
+    A = rng.random((M, K)) * np.exp2(rng.integers(-30, 30, size=(M, 1)))
+    B = rng.random((K, N)) * np.exp2(rng.integers(-30, 30, size=(1, N)))
+    div = rng.integers(0, 3, size=M).astype(np.int32)
+    flag = rng.integers(0, 2, size=N).astype(np.int32)
+    dA, dB = ss.DMat.from_host(ctx, A if op == "N" else A.T), ss.DMat.from_host(ctx, B)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, None, None, SS_PRECISION_F64_INT8))
+    want = (A.astype(np.longdouble) @ B.astype(np.longdouble)).astype(float)
+    assert np.max(np.abs(dC.to_host() - want) / want) < RTOL
+    dd, df = ss.DIVec.from_host(ctx, div), ss.DIVec.from_host(ctx, flag)
+    check(ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, dd.h, df.h, SS_PRECISION_F64_INT8))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = np.where(div[:, None] == 0, 0.0, want / div[:, None].astype(float))
+    ref[:, flag == 0] = -99.0
+    got = dC.to_host()
+    assert np.array_equal(got == -99, ref == -99) and np.array_equal(got == 0, ref == 0)
+    nz = (ref != 0) & (ref != -99)
+    assert not nz.any() or np.max(np.abs(got[nz] - ref[nz]) / ref[nz]) < RTOL
+    # negative / non-finite operands are refused (the slicing is defined for non-negative graphs)
+    A[M // 2, K // 2] = -1.0
+    dA = ss.DMat.from_host(ctx, A if op == "N" else A.T)
+    st = ss.lib().ss_gemm_lowp(ctx.h, o_, dA.h, dB.h, dC.h, None, None, SS_PRECISION_F64_INT8)
+    assert st == 6 and b"non-negative" in ss.lib().ss_last_error()
+
+
+def test_predict_f64_int8_mode_against_oracle(ss, o):
+    S, Yfull = _enzyme_like(o, seed=6)
+    N, Nt = Yfull.shape
+    names = [f"D{i:04d}" for i in range(N)]
+    tn = [f"T{j:04d}" for j in range(Nt)]
+    DT = ss.NamedArray(Yfull, (names, tn))
+    for weighted, alpha in ((True, 0.2), (False, 0.35)):
+        X = ss.featurize(ss.NamedArray(S, (names, names)), alpha, weighted)
+        q = names[::9]
+        A, B = ss.construct(DT, X, q)
+        got = ss.predict((A, B), DT[q, tn], precision="f64_int8", clean=True)
+        Ao, Bo, nn = o.construct_queries(Yfull, (names, tn), X.array, (names, X.names(2)), q)
+        want = o.predict_dense(Ao, Bo, nn, q, tn)
+        o.clean(want, Ao, nn, tn)
+        assert relerr(got.array, want) < RTOL and np.array_equal(got.array == -99, want == -99)
