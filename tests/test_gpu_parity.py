@@ -722,3 +722,37 @@ def test_predict_f64_int8_mode_against_oracle(ss, o):
         want = o.predict_dense(Ao, Bo, nn, q, tn)
         o.clean(want, Ao, nn, tn)
         assert relerr(got.array, want) < RTOL and np.array_equal(got.array == -99, want == -99)
+
+
+def test_two_layer_nbi_recommender_shape(ss, o):
+    """BASELINE config 5's form (scaled down): classical 2-layer NBI, no feature layer --
+    F[s,t] = Y * U, U = (Y' ./ kt) * (Y ./ ks) (reference src/core.jl:446-466 on a graph without
+    features), followed by per-user top-L."""
+    from simspread_b200._lib import check
+    rng = np.random.default_rng(55)
+    users, items = 700, 420
+    Y = (rng.random((users, items)) < 0.02).astype(float)
+    Y[:, 7] = 0.0   # an item nobody has
+    Y[11, :] = 0.0  # a user without items
+    ctx = ss.Context.default()
+    dY, R = ss.DMat.from_host(ctx, Y), ss.DMat(ctx, users, items)
+    check(ss.lib().ss_predict_source(ctx.h, None, dY.h, R.h, 0))
+    ks, kt = Y.sum(1), Y.sum(0)
+    Wst = o._div_rows(Y, ks.astype(np.int64))
+    U = o._div_rows(np.ascontiguousarray(Y.T), kt.astype(np.int64)) @ Wst
+    want = Y @ U
+    # literal reference path on the (users + items)^2 adjacency matrix
+    n = users + items
+    A = np.zeros((n, n))
+    A[:users, users:] = Y
+    A[users:, :users] = Y.T
+    names = [f"n{i}" for i in range(n)]
+    lit = o.predict_dense_single(A, names, names[:users], names[users:])
+    assert relerr(want, lit) < 1e-12
+    got = R.to_host()
+    assert relerr(got, lit) < RTOL
+    L = 20
+    idx = ss.DIVec(ctx, L * users)
+    check(ss.lib().ss_topl_rows(ctx.h, R.h, L, idx.h, None))
+    order = np.stack([o.sortperm_rev(got[u])[:L] for u in range(users)])
+    assert np.array_equal(idx.to_host().reshape(users, L), order)

@@ -1,0 +1,64 @@
+"""Wall-clock of the other BASELINE configs through the public host API (they are parity-test cases,
+not the bench line): C2 = Enzyme-shaped 10-fold CV, C3 = 21-point alpha sweep on 5k queries x 2k
+targets.  The CPU oracle's literal path is timed on C2 (all folds) for scale.  Writes
+gpurun_out/configs.json; run under gpurun."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simspread_b200 as ss
+from oracle import simspread_oracle as o
+
+out = {}
+rng = np.random.default_rng(20241)
+N, Nt = 445, 664
+S = np.round(rng.beta(2, 5, size=(N, N)), 6)
+np.fill_diagonal(S, 1.0)
+Y = (rng.random((N, Nt)) < 0.0099).astype(float)
+names = [f"D{i:04d}" for i in range(N)]
+tn = [f"T{j:04d}" for j in range(Nt)]
+DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Y, (names, tn))
+ss.cross_validate(DT, DD, 0.35, weighted=False, k_=10, seed=1)  # warm-up (context, workspaces)
+ts = []
+for _ in range(5):
+    t0 = time.perf_counter()
+    res = ss.cross_validate(DT, DD, 0.35, weighted=False, k_=10, seed=1)
+    ts.append(time.perf_counter() - t0)
+t_gpu = float(np.median(ts))
+folds = res["folds"]
+t0 = time.perf_counter()
+Xo, xr, xc = o.featurize(S, names, names, 0.35, False)
+for q in folds:
+    Ao, Bo, nn = o.construct_queries(Y, (names, tn), Xo, (xr, xc), q)
+    w = o.predict_dense(Ao, Bo, nn, q, tn)
+    o.clean(w, Ao, nn, tn)
+t_cpu = time.perf_counter() - t0
+out["C2_enzyme_10fold_cv"] = {"shape": [N, Nt], "alpha": 0.35, "weighted": False, "gpu_wall_s_median_of_5": t_gpu,
+                              "scores_per_s": N * Nt / t_gpu, "cpu_oracle_literal_wall_s": t_cpu,
+                              "cpu_cores": os.cpu_count(), "AuROC": res["AuROC"], "AuPRC": res["AuPRC"],
+                              "includes": "upload, featurize, 10 x (gather, predict+clean), AuROC/AuPRC, recall/precision@20, download"}
+print(json.dumps(out["C2_enzyme_10fold_cv"]), flush=True)
+
+nq, ns, nt = 5000, 5000, 2000
+Nn = nq + ns
+S3 = np.round(rng.random((Nn, Nn)), 6)
+Y3 = (rng.random((Nn, nt)) < 0.01).astype(float)
+n3 = [f"n{i}" for i in range(Nn)]
+t3 = [f"t{j}" for j in range(nt)]
+DD3, DT3 = ss.NamedArray(S3, (n3, n3)), ss.NamedArray(Y3, (n3, t3))
+alphas = [round(0.05 * i, 2) for i in range(21)]
+ss.alpha_sweep(DT3, DD3, n3[:nq], alphas[:2])
+t0 = time.perf_counter()
+sw = ss.alpha_sweep(DT3, DD3, n3[:nq], alphas)
+t_sw = time.perf_counter() - t0
+out["C3_alpha_sweep_21_points"] = {"shape": {"nq": nq, "ns": ns, "nt": nt}, "gpu_wall_s": t_sw,
+                                   "scores_per_s": 21 * nq * nt / t_sw, "points": sw,
+                                   "note": "dense DMMA chain for every alpha (alpha_sweep gathers dense blocks); "
+                                           "the sparse chain is selected by predict(layout='auto')"}
+print(json.dumps({k: v for k, v in out["C3_alpha_sweep_21_points"].items() if k != "points"}), flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
