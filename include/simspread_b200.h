@@ -95,6 +95,8 @@ SS_API int32_t ss_host_free(void* p);
 /* ---- device containers ------------------------------------------------------------------- */
 /* zero-initialised rows x cols matrix; ld is padded to a multiple of 16 elements (TMA alignment) */
 SS_API int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out);
+/* same, allocated with cudaMalloc so that ss_mat_ipc_handle() can export it to peer processes */
+SS_API int32_t ss_mat_create_ipc(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out);
 /* non-owning view of caller-managed device memory (ld >= rows).  GEMM inputs additionally need a
  * 16-byte aligned base and an even ld (TMA); a GEMM output may be a row-offset view (8-byte aligned). */
 SS_API int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols, int64_t ld, ss_mat** out);

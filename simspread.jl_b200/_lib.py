@@ -41,6 +41,7 @@ SIGNATURES = {
     "ss_host_alloc": (c_i32, [c_i64, P(vp)]),
     "ss_host_free": (c_i32, [vp]),
     "ss_mat_create": (c_i32, [vp, c_i64, c_i64, P(vp)]),
+    "ss_mat_create_ipc": (c_i32, [vp, c_i64, c_i64, P(vp)]),
     "ss_mat_wrap": (c_i32, [vp, vp, c_i64, c_i64, c_i64, P(vp)]),
     "ss_mat_destroy": (c_i32, [vp]),
     "ss_mat_info": (c_i32, [vp, P(c_i64), P(c_i64), P(c_i64), P(vp)]),

@@ -172,7 +172,7 @@ int32_t ss_host_free(void* p) {
 
 // ---- containers ------------------------------------------------------------------------------
 
-int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
+static int32_t mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out, bool ipc) {
     SS_ENTER(ctx);
     SS_REQUIRE(out && rows >= 0 && cols >= 0, "ss_mat_create: bad shape %lld x %lld", (long long)rows,
                (long long)cols);
@@ -183,17 +183,29 @@ int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
     m->ld = round_up(rows > 0 ? rows : 1, 16);
     m->owned = true;
     const size_t bytes = size_t(m->ld) * size_t(cols > 0 ? cols : 1) * 8 + 256;
-    cudaError_t e = cudaMalloc(&m->d, bytes);
+    // stream-ordered pool allocation: no device-wide synchronisation per matrix (CV loops create
+    // and drop many small blocks); ss_mat_create_ipc() is the cudaMalloc variant for IPC sharing
+    cudaError_t e = ipc ? cudaMalloc(&m->d, bytes)
+                        : cudaMallocAsync(reinterpret_cast<void**>(&m->d), bytes, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         delete m;
-        set_error("ss_mat_create: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        set_error("ss_mat_create: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return SS_ERR_OOM;
     }
+    m->pooled = !ipc;
     SS_CHECK_CUDA(cudaMemsetAsync(m->d, 0, bytes, ctx->stream));
-    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ipc) SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = m;
     return SS_OK;
+}
+
+int32_t ss_mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
+    return mat_create(ctx, rows, cols, out, false);
+}
+
+int32_t ss_mat_create_ipc(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out) {
+    return mat_create(ctx, rows, cols, out, true);
 }
 
 int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols, int64_t ld, ss_mat** out) {
@@ -216,7 +228,8 @@ int32_t ss_mat_destroy(ss_mat* m) {
     if (!m) return SS_OK;
     if (m->owned && m->d) {
         cudaSetDevice(m->ctx->device);
-        cudaFree(m->d);
+        if (m->pooled) cudaFreeAsync(m->d, m->ctx->stream);
+        else cudaFree(m->d);
     }
     delete m;
     return SS_OK;
@@ -285,15 +298,14 @@ int32_t ss_ivec_create(ss_ctx* ctx, int64_t n, ss_ivec** out) {
     v->n = n;
     v->owned = true;
     const size_t bytes = size_t(n > 0 ? n : 1) * 4 + 64;
-    cudaError_t e = cudaMalloc(&v->d, bytes);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&v->d), bytes, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         delete v;
-        set_error("ss_ivec_create: cudaMalloc of %zu bytes failed", bytes);
+        set_error("ss_ivec_create: allocation of %zu bytes failed", bytes);
         return SS_ERR_OOM;
     }
     SS_CHECK_CUDA(cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
-    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = v;
     return SS_OK;
 }
@@ -314,7 +326,7 @@ int32_t ss_ivec_destroy(ss_ivec* v) {
     if (!v) return SS_OK;
     if (v->owned && v->d) {
         cudaSetDevice(v->ctx->device);
-        cudaFree(v->d);
+        cudaFreeAsync(v->d, v->ctx->stream);
     }
     delete v;
     return SS_OK;
@@ -545,7 +557,7 @@ int32_t ss_gemm_f64_mirrored(ss_ctx* ctx, int32_t opA, const ss_mat* A, const ss
 int32_t ss_mat_ipc_handle(ss_ctx* ctx, const ss_mat* m, void* handle64_out) {
     SS_ENTER(ctx);
     SS_REQUIRE(m && handle64_out, "ss_mat_ipc_handle: null argument");
-    SS_REQUIRE(m->owned, "ss_mat_ipc_handle: only library-owned matrices (ss_mat_create) can be shared");
+    SS_REQUIRE(m->owned && !m->pooled, "ss_mat_ipc_handle: only matrices from ss_mat_create_ipc can be shared");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     SS_CHECK_CUDA(cudaIpcGetMemHandle(&h, m->d));

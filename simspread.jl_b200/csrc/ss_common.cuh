@@ -72,6 +72,7 @@ struct ss_mat {
     double* d = nullptr;
     int64_t rows = 0, cols = 0, ld = 0;
     bool owned = false;
+    bool pooled = false;  // allocated with cudaMallocAsync on the context stream
 };
 
 struct ss_ivec {

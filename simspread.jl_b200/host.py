@@ -82,11 +82,12 @@ def _f64_colmajor(a) -> np.ndarray:
 class DMat:
     """Device matrix handle (`ss_mat`), column-major float64."""
 
-    def __init__(self, ctx: Context, rows: int, cols: int):
+    def __init__(self, ctx: Context, rows: int, cols: int, ipc: bool = False):
         self.ctx = ctx
         self.rows, self.cols = int(rows), int(cols)
         h = C.c_void_p()
-        check(lib().ss_mat_create(ctx.h, self.rows, self.cols, C.byref(h)))
+        fn = lib().ss_mat_create_ipc if ipc else lib().ss_mat_create
+        check(fn(ctx.h, self.rows, self.cols, C.byref(h)))
         self.h = h
 
     @classmethod

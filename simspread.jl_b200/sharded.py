@@ -115,7 +115,7 @@ class LibBackend:
         self.tktl = torch.zeros(p.nt_blk, dtype=torch.int32, device=dev)
         # T is library-owned (plain cudaMalloc) so that its IPC handle can be mapped by the peers;
         # bT is a torch view of the same memory (checks, NCCL fallback).
-        self.mTfull = ss.DMat(ctx, nf, p.nt_padded)
+        self.mTfull = ss.DMat(ctx, nf, p.nt_padded, ipc=True)
         _, _, ldt_, pT = self.mTfull.info()
         assert ldt_ == self.ldt
         self.bT = torch.as_tensor(_CudaView(pT, (p.nt_padded, self.ldt)), device=dev)
