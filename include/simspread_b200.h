@@ -131,6 +131,10 @@ SS_API int32_t ss_featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, int3
 SS_API int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values);
 SS_API int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t* col_idx, double* values);
 SS_API int32_t ss_csr_destroy(ss_csr* c);
+/* non-owning CSR over caller-managed device arrays (int32 row_ptr[rows+1], col_idx[nnz] ascending
+ * within a row, optional float64 values[nnz]; values == NULL means every stored entry is 1.0) */
+SS_API int32_t ss_csr_wrap(ss_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, void* row_ptr_dev, void* col_idx_dev,
+                           void* values_dev, ss_csr** out);
 
 /* ---- (2) graph construction + degrees ------------------------------------------------------ */
 /* Block extraction of construct() [src/core.jl:167,171-172: X[queries,features], X[sources,features],
@@ -185,6 +189,13 @@ SS_API int32_t ss_predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr*
 /* predict(A, ytrain) / source rows [src/core.jl:446-466]: R = Xs*T + Y*U, U = (Y' ./ kt)*(Y ./ ks).
  * Xs may be NULL (classical 2-layer NBI: R = Y*U). */
 SS_API int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags);
+/* Sparse 2-layer NBI with fused top-L (BASELINE config 5; predict(A, ytrain) of src/core.jl:446-466
+ * on the graph [0 Y; Y' 0], reduced to `sortperm(rev=true)[1:L]` per source, src/performance.jl:315):
+ * Y = CSR of the source x target graph, YT = CSR of its transpose.  F is never materialised.  Sources
+ * [s_begin, s_end) are processed (shard the range across GPUs); idx_out is L x sources (0-based target
+ * indices, -1 padding), val_out (optional) the matching scores, dense L x sources with ld == L.  L <= 32. */
+SS_API int32_t ss_recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int32_t L, int64_t s_begin,
+                                 int64_t s_end, ss_ivec* idx_out, ss_mat* val_out);
 /* clean! [src/core.jl:478-484]: R[:,t] = -99 for every t with kt[t] == 0. */
 SS_API int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt);
 

@@ -13,7 +13,7 @@ from .namedarray import NamedArray  # noqa: F401
 from .host import (  # noqa: F401
     AuPRC, AuROC, BEDROC, Context, alpha_sweep, cross_validate, DCsr, DIVec, DMat, Graph, accuracy, balancedaccuracy, clean_, construct, cutoff,
     cutoff_, f1score, featurize, featurize_, k, mcc, maxperformance, meanperformance, meanstdperformance, precision, precisionatL, predict, recall,
-    recallatL, save, split, spread, validity_ratio,
+    recallatL, recommend_topl, save, split, spread, validity_ratio,
 )
 from ._build import build, lib_path  # noqa: F401
 

@@ -407,11 +407,48 @@ int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t*
 int32_t ss_csr_destroy(ss_csr* c) {
     if (!c) return SS_OK;
     cudaSetDevice(c->ctx->device);
-    // stream-ordered pool allocations (cudaMallocAsync): no device-wide synchronisation per CSR
-    if (c->row_ptr) cudaFreeAsync(c->row_ptr, c->ctx->stream);
-    if (c->col_idx) cudaFreeAsync(c->col_idx, c->ctx->stream);
-    if (c->values) cudaFreeAsync(c->values, c->ctx->stream);
+    if (c->owned) {  // stream-ordered pool allocations (cudaMallocAsync): no device-wide synchronisation per CSR
+        if (c->row_ptr) cudaFreeAsync(c->row_ptr, c->ctx->stream);
+        if (c->col_idx) cudaFreeAsync(c->col_idx, c->ctx->stream);
+        if (c->values) cudaFreeAsync(c->values, c->ctx->stream);
+    }
     delete c;
+    return SS_OK;
+}
+
+int32_t ss_csr_wrap(ss_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, void* row_ptr_dev, void* col_idx_dev,
+                    void* values_dev, ss_csr** out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(out && rows >= 0 && cols >= 0 && nnz >= 0 && row_ptr_dev && (nnz == 0 || col_idx_dev),
+               "ss_csr_wrap: bad argument");
+    SS_REQUIRE(nnz < (1ll << 31) && cols < (1ll << 31), "ss_csr_wrap: int32 CSR limits exceeded");
+    ss_csr* c = new ss_csr();
+    c->ctx = ctx;
+    c->rows = rows;
+    c->cols = cols;
+    c->nnz = nnz;
+    c->row_ptr = static_cast<int32_t*>(row_ptr_dev);
+    c->col_idx = static_cast<int32_t*>(col_idx_dev);
+    c->values = static_cast<double*>(values_dev);
+    c->owned = false;
+    *out = c;
+    return SS_OK;
+}
+
+int32_t ss_recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int32_t L, int64_t s_begin, int64_t s_end,
+                          ss_ivec* idx_out, ss_mat* val_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Y && YT && idx_out, "ss_recommend_topl: null argument");
+    SS_REQUIRE(YT->rows == Y->cols && YT->cols == Y->rows && YT->nnz == Y->nnz,
+               "ss_recommend_topl: YT must be the CSR of the transpose of Y");
+    SS_REQUIRE((Y->values == nullptr) == (YT->values == nullptr), "ss_recommend_topl: Y and YT must both be binary or both weighted");
+    SS_REQUIRE(L >= 1 && L <= 32 && L <= Y->cols, "ss_recommend_topl: L must be in 1..min(32, targets)");
+    SS_REQUIRE(s_begin >= 0 && s_end <= Y->rows && s_begin <= s_end, "ss_recommend_topl: bad source range");
+    SS_REQUIRE(idx_out->n == int64_t(L) * Y->rows, "ss_recommend_topl: idx_out must hold L x sources entries");
+    SS_REQUIRE(!val_out || (val_out->rows == L && val_out->cols == Y->rows && val_out->ld == L),
+               "ss_recommend_topl: val_out must be a dense L x sources matrix with ld == L");
+    SS_TRY(recommend_topl(ctx, Y, YT, L, s_begin, s_end, idx_out->d, val_out ? val_out->d : nullptr));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }
 

@@ -88,6 +88,7 @@ struct ss_csr {
     int32_t* row_ptr = nullptr;  // rows + 1
     int32_t* col_idx = nullptr;  // nnz
     double* values = nullptr;    // nnz or null
+    bool owned = true;           // false: wraps caller-managed device arrays (ss_csr_wrap)
 };
 
 namespace ss {
@@ -125,6 +126,8 @@ int32_t atl(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int L, double* out2);
 int32_t auroc_auprc(ss_ctx* ctx, const uint8_t* labels, const double* scores, int64_t M,
                     double* out2);
 int32_t auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, double* out2);
+int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
+                       int32_t* idx_out, double* val_out);
 int32_t threshold_sweep(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int metric, double* out4);
 int32_t bedroc(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int rev, double alpha, double* out);
 

@@ -900,3 +900,32 @@ def save(filepath: str, *args, delimiter: str = "\t") -> None:
             for ti, t in enumerate(targets):
                 row = [_jl_string(fold), '"' + q + '"', '"' + t + '"', _jl_string(yh[qi, ti]), _jl_string(yy[qi, ti])]
                 f.write(delimiter.join(row) + "\n")
+
+
+def recommend_topl(y, L: int = 20, weighted: Optional[bool] = None, s_range: Optional[Tuple[int, int]] = None):
+    """Top-L targets per source of the classical 2-layer NBI (`predict(construct(y, X), y)` of the
+    reference with an empty feature layer, src/core.jl:446-466, ranked as in src/performance.jl:315),
+    computed from the sparse graph without materialising the score matrix (BASELINE config 5).
+    `y`: NamedArray / dense matrix (sources x targets).  Returns (idx, val): (sources, L) arrays of
+    0-based target indices (-1 padding) and scores.  `s_range=(begin, end)` restricts the sources
+    (multi-GPU sharding by source rows)."""
+    ctx = Context.default()
+    arr = y.array if isinstance(y, NamedArray) else np.asarray(y)
+    ns, nt = arr.shape
+    if weighted is None:
+        weighted = bool(np.any((arr != 0) & (arr != 1)))
+    d = DMat.from_host(ctx, arr)
+    tiny = 5e-324  # keep every positive entry
+    cy = DCsr.from_dense(ctx, d, tiny if not weighted else float("-inf"), weighted)
+    cyt = DCsr.from_dense(ctx, d, tiny if not weighted else float("-inf"), weighted, by_columns=True)
+    idx = DIVec(ctx, L * ns)
+    val = DMat(ctx, L, ns)
+    _, _, ldv, _ = val.info()
+    b, e = s_range if s_range is not None else (0, ns)
+    if ldv == L:
+        check(lib().ss_recommend_topl(ctx.h, cy.h, cyt.h, int(L), int(b), int(e), idx.h, val.h))
+        v = val.to_host().T
+    else:  # L not a multiple of the 16-element row padding: indices only, scores re-read by the caller
+        check(lib().ss_recommend_topl(ctx.h, cy.h, cyt.h, int(L), int(b), int(e), idx.h, None))
+        v = None
+    return idx.to_host().reshape(ns, L), v

@@ -756,3 +756,36 @@ def test_two_layer_nbi_recommender_shape(ss, o):
     check(ss.lib().ss_topl_rows(ctx.h, R.h, L, idx.h, None))
     order = np.stack([o.sortperm_rev(got[u])[:L] for u in range(users)])
     assert np.array_equal(idx.to_host().reshape(users, L), order)
+
+
+@pytest.mark.parametrize("users,items,dens,L", [(300, 200, 0.05, 16), (1000, 2600, 0.01, 16), (64, 40000, 0.002, 32)])
+def test_sparse_recommender_topl_against_dense_path(ss, o, users, items, dens, L):
+    """Config-5 form at test scale: two-hop CSR expansion with L2-resident accumulators and fused
+    top-L, against the dense chain (ss_predict_source) + ss_topl_rows and the oracle."""
+    from simspread_b200._lib import check
+    rng = np.random.default_rng(users + items)
+    mask = rng.random((users, items)) < dens
+    ctx = ss.Context.default()
+    for weighted in (True, False):
+        Y = np.where(mask, np.round(rng.random((users, items)) + 0.5, 3), 0.0) if weighted else mask.astype(float)
+        Y[min(3, users - 1), :] = 0.0  # a user without items: all scores 0 -> first L columns
+        idx, val = ss.recommend_topl(Y, L)
+        ks = np.count_nonzero(Y, axis=1)
+        kt = np.count_nonzero(Y, axis=0)
+        U = o._div_rows(np.ascontiguousarray(Y.T), kt) @ o._div_rows(Y, ks)
+        F = Y @ U
+        want_val = -np.sort(-F, axis=1)[:, :L]
+        got_val = np.take_along_axis(F, np.maximum(idx, 0), axis=1)
+        assert idx.min() >= 0 and idx.max() < items
+        # the selected scores are the L largest (element-wise within the FP64 tolerance) ...
+        assert np.allclose(val, want_val, rtol=1e-12, atol=1e-300)
+        assert np.allclose(got_val, want_val, rtol=1e-12, atol=1e-300)
+        # ... in descending order, without duplicates
+        assert np.all(val[:, :-1] >= val[:, 1:])
+        assert all(len(set(r)) == L for r in idx)
+        if weighted:  # no exact ties between non-zero scores: the order itself must match the reference order
+            order = np.stack([o.sortperm_rev(F[u])[:L] for u in range(users)])
+            distinct = np.abs(np.diff(want_val, axis=1)) > 1e-9 * np.abs(want_val[:, :-1])
+            rows_ok = distinct.all(axis=1) & (want_val[:, -1] > 0)
+            assert rows_ok.sum() > 0 and np.array_equal(idx[rows_ok], order[rows_ok])
+        assert np.array_equal(idx[min(3, users - 1)], np.arange(L))  # all-zero row: stable order = first L columns

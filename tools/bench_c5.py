@@ -1,0 +1,94 @@
+"""BASELINE config 5 at full scale on one B200: recommender-shaped sparse graph, 2 000 000 users x
+500 000 items, each entry Bernoulli(1e-4) (~1e8 edges), 2-layer NBI scores reduced on the fly to the
+top-20 items per user (ss_recommend_topl).  The graph is generated on the device with torch and
+wrapped (ss_csr_wrap); a few users are re-computed with torch sparse mat-vecs as a spot check.
+Usage: python tools/bench_c5.py [users] [items] [user_fraction]   -> gpurun_out/c5.json"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simspread_b200 as ss
+from simspread_b200._lib import check
+
+ns = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+nt = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
+frac = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+dens, L = 1e-4, 20
+dev = torch.device("cuda:0")
+ctx = ss.Context(0)
+lib = ss.lib()
+g = torch.Generator(device=dev)
+g.manual_seed(20245)
+# Bernoulli(dens) graph: Binomial row degrees ~ Poisson(nt*dens), uniform columns, duplicates removed
+deg = torch.poisson(torch.full((ns,), nt * dens, device=dev), generator=g).to(torch.int64)
+rows = torch.repeat_interleave(torch.arange(ns, device=dev), deg)
+cols = torch.randint(0, nt, (rows.numel(),), device=dev, generator=g)
+keys = torch.unique(rows * nt + cols)  # sorted: by row, then column
+rows, cols = keys // nt, keys % nt
+nnz = keys.numel()
+y_ptr = torch.zeros(ns + 1, dtype=torch.int32, device=dev)
+y_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=ns), 0).to(torch.int32)
+y_idx = cols.to(torch.int32)
+keyt = torch.sort(cols * ns + rows).values
+yt_ptr = torch.zeros(nt + 1, dtype=torch.int32, device=dev)
+yt_ptr[1:] = torch.cumsum(torch.bincount(keyt // ns, minlength=nt), 0).to(torch.int32)
+yt_idx = (keyt % ns).to(torch.int32)
+del keys, keyt, rows, cols
+torch.cuda.synchronize()
+
+
+def wrap(r, c, n, ptr, idx):
+    h = C.c_void_p()
+    check(lib.ss_csr_wrap(ctx.h, r, c, n, C.c_void_p(ptr.data_ptr()), C.c_void_p(idx.data_ptr()), None, C.byref(h)))
+    return h
+
+
+hY, hYT = wrap(ns, nt, nnz, y_ptr, y_idx), wrap(nt, ns, nnz, yt_ptr, yt_idx)
+idx = torch.full((ns, L), -2, dtype=torch.int32, device=dev)
+val = torch.zeros((ns, L), dtype=torch.float64, device=dev)
+vi, vm = C.c_void_p(), C.c_void_p()
+check(lib.ss_ivec_wrap(ctx.h, C.c_void_p(idx.data_ptr()), ns * L, C.byref(vi)))
+check(lib.ss_mat_wrap(ctx.h, C.c_void_p(val.data_ptr()), L, ns, L, C.byref(vm)))
+s_end = max(64, int(ns * frac))
+check(lib.ss_recommend_topl(ctx.h, hY, hYT, L, 0, min(2048, s_end), vi, vm))  # warm-up
+ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+l0 = ctx.launch_count()
+t0 = time.perf_counter()
+e0.record(ext)
+check(lib.ss_recommend_topl(ctx.h, hY, hYT, L, 0, s_end, vi, vm))
+e1.record(ext)
+ctx.sync()
+wall = time.perf_counter() - t0
+ms = e0.elapsed_time(e1)
+# partial products of the processed users: sum_{t' in Y[s]} sum_{s' in YT[t']} deg(s')
+ks = (y_ptr[1:] - y_ptr[:-1]).to(torch.float64)
+kt = (yt_ptr[1:] - yt_ptr[:-1]).to(torch.float64)
+per_item = torch.zeros(nt, dtype=torch.float64, device=dev).index_add_(0, y_idx.long(), ks.repeat_interleave((y_ptr[1:] - y_ptr[:-1]).long()))
+pp = float(per_item[y_idx[: int(y_ptr[s_end])].long()].sum().item())
+# spot check: three users recomputed with torch sparse mat-vecs
+Ysp = torch.sparse_csr_tensor(y_ptr.long(), y_idx.long(), torch.ones(nnz, dtype=torch.float64, device=dev), size=(ns, nt))
+YTsp = torch.sparse_csr_tensor(yt_ptr.long(), yt_idx.long(), torch.ones(nnz, dtype=torch.float64, device=dev), size=(nt, ns))
+worst = 0.0
+for s in (0, s_end // 2, s_end - 1):
+    a = torch.zeros(nt, dtype=torch.float64, device=dev)
+    a[y_idx[y_ptr[s]:y_ptr[s + 1]].long()] = 1.0
+    v1 = torch.where(kt > 0, a / kt, torch.zeros_like(a))
+    v2 = torch.mv(Ysp, v1)
+    F = torch.mv(YTsp, torch.where(ks > 0, v2 / ks, torch.zeros_like(v2)))
+    want = torch.sort(F, descending=True).values[:L]
+    got = val[s]
+    worst = max(worst, float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item()))
+    assert bool((F[idx[s].long()] - got).abs().max() <= 1e-12 * got.abs().max().clamp_min(1e-300))
+out = {"users": ns, "items": nt, "edges": nnz, "L": L, "users_processed": s_end, "ms": ms, "wall_s": wall,
+       "scores_per_s": s_end * nt / (ms * 1e-3), "partial_products": pp,
+       "partial_products_per_s": pp / (ms * 1e-3), "achieved_gbs_4B_per_pp": pp * 4 / (ms * 1e-3) / 1e9,
+       "kernel_launches": ctx.launch_count() - l0, "spot_check_max_rel_err_top20": worst}
+print(json.dumps(out))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/c5.json", "w"), indent=1)
