@@ -128,6 +128,19 @@ SS_API int32_t ss_featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, int3
 /* Same, but the CSR of S' (one CSR row per COLUMN of S, ascending row index) -- the natural
  * direction for a column-major S and the form the sparse chain needs for Xs (features x sources). */
 SS_API int32_t ss_featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t weighted, ss_csr** out);
+/* Upstream similarity fused with the threshold: the tutorial's
+ * `S = 1 .- pairwise(Jaccard(), X, dims=1)` (docs/src/tutorial/fishers-flowers.jl:66, Distances.jl) followed by
+ * `featurize(S[rows, cols], alpha, weighted)` (src/core.jl:106-112) in one kernel; S is never materialised.
+ * DA: na x d and DB: nb x d descriptor matrices (entities in rows); X: na x nb,
+ * X[i,j] = cutoff(1 - (1 - a1/a2), alpha, weighted) with Distances.jl's accumulation a1 = sum_k |a+b| - |a-b|,
+ * a2 = sum_k |a+b| + |a-b| (k ascending); 0/0 counts as distance 0.  Bit-exact against the shipped iris.simmat. */
+SS_API int32_t ss_jaccard_featurize(ss_ctx* ctx, const ss_mat* DA, const ss_mat* DB, double alpha, int32_t weighted,
+                                    ss_mat* X);
+/* Same for bit-packed fingerprints (the Jaccard index of 0/1 descriptors = Tanimoto coefficient):
+ * fa_dev / fb_dev are device arrays of na x words / nb x words uint64, row-major, one fingerprint per row;
+ * X[i,j] = cutoff(|a & b| / |a | b|, alpha, weighted). */
+SS_API int32_t ss_tanimoto_featurize_bits(ss_ctx* ctx, const void* fa_dev, int64_t na, const void* fb_dev, int64_t nb,
+                                          int64_t words, double alpha, int32_t weighted, ss_mat* X);
 SS_API int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values);
 SS_API int32_t ss_csr_download(ss_ctx* ctx, const ss_csr* c, int32_t* row_ptr, int32_t* col_idx, double* values);
 SS_API int32_t ss_csr_destroy(ss_csr* c);

@@ -590,6 +590,46 @@ def meanstdperformance(y, yhat, metric):
 
 
 # --------------------------------------------------------------------------------------------
+# upstream similarity (not in src/: the tutorial's user-side step, docs/src/tutorial/fishers-flowers.jl:66)
+# --------------------------------------------------------------------------------------------
+
+
+def jaccard_similarity(XA: np.ndarray, XB: np.ndarray) -> np.ndarray:
+    """`1 .- pairwise(Jaccard(), X, dims=1)` (docs/src/tutorial/fishers-flowers.jl:66) between the rows of
+    XA and XB.  Distances.jl is not in the tree (a docs dependency); its Jaccard distance accumulates, over
+    the descriptors in ascending order, a1 += |x+y| - |x-y| (= 2 min) and a2 += |x+y| + |x-y| (= 2 max) and
+    returns 1 - a1/a2, a NaN result (0/0) being replaced by 0.  Pinned BIT-EXACTLY by the shipped
+    docs/src/tutorial/data/iris.simmat (= this function of iris.features), see tests/test_oracle_golden.py."""
+    XA = np.asarray(XA, dtype=np.float64)
+    XB = np.asarray(XB, dtype=np.float64)
+    a1 = np.zeros((XA.shape[0], XB.shape[0]))
+    a2 = np.zeros_like(a1)
+    for kk in range(XA.shape[1]):
+        m = np.abs(XA[:, None, kk] - XB[None, :, kk])
+        p_ = np.abs(XA[:, None, kk] + XB[None, :, kk])
+        a1 += p_ - m
+        a2 += p_ + m
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dist = 1.0 - a1 / a2
+    dist = np.where(np.isnan(dist), 0.0, dist)
+    return 1.0 - dist
+
+
+def tanimoto_bits(FA: np.ndarray, FB: np.ndarray) -> np.ndarray:
+    """Jaccard index of 0/1 descriptors given as bit-packed uint64 rows: |a & b| / |a | b| (0/0 -> 1,
+    the distance-0 convention above)."""
+    FA = np.asarray(FA, dtype=np.uint64)
+    FB = np.asarray(FB, dtype=np.uint64)
+    ba = np.unpackbits(FA.view(np.uint8), axis=1).astype(np.int64)
+    bb = np.unpackbits(FB.view(np.uint8), axis=1).astype(np.int64)
+    both = ba @ bb.T
+    union = ba.sum(1)[:, None] + bb.sum(1)[None, :] - both
+    with np.errstate(invalid="ignore", divide="ignore"):
+        s_ = both.astype(np.float64) / union.astype(np.float64)
+    return np.where(union == 0, 1.0, s_)
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic workloads (SURVEY.md 8d) -- shared by tests and bench so both arms see the same data
 # --------------------------------------------------------------------------------------------
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "ss_featurize": (c_i32, [vp, vp, c_f64, c_i32, vp]),
     "ss_featurize_csr": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),
     "ss_featurize_csc": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),
+    "ss_jaccard_featurize": (c_i32, [vp, vp, vp, c_f64, c_i32, vp]),
+    "ss_tanimoto_featurize_bits": (c_i32, [vp, vp, c_i64, vp, c_i64, c_i64, c_f64, c_i32, vp]),
     "ss_csr_info": (c_i32, [vp, P(c_i64), P(c_i64), P(c_i64), P(c_i32)]),
     "ss_csr_download": (c_i32, [vp, vp, vp, vp, vp]),
     "ss_csr_destroy": (c_i32, [vp]),

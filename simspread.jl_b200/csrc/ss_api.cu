@@ -382,6 +382,31 @@ int32_t ss_featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, int32_t wei
     return SS_OK;
 }
 
+int32_t ss_jaccard_featurize(ss_ctx* ctx, const ss_mat* DA, const ss_mat* DB, double alpha, int32_t weighted, ss_mat* X) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(DA && DB && X, "ss_jaccard_featurize: null matrix");
+    SS_REQUIRE(DA->cols == DB->cols, "ss_jaccard_featurize: descriptor counts differ (%lld vs %lld)", (long long)DA->cols,
+               (long long)DB->cols);
+    SS_REQUIRE(X->rows == DA->rows && X->cols == DB->rows, "ss_jaccard_featurize: X must be rows(DA) x rows(DB)");
+    SS_TRY(jaccard_featurize(ctx, DA, DB, alpha, weighted != 0, X));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t ss_tanimoto_featurize_bits(ss_ctx* ctx, const void* fa_dev, int64_t na, const void* fb_dev, int64_t nb, int64_t words,
+                                   double alpha, int32_t weighted, ss_mat* X) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(X && na >= 0 && nb >= 0 && words >= 1, "ss_tanimoto_featurize_bits: bad argument");
+    SS_REQUIRE((fa_dev || na == 0) && (fb_dev || nb == 0), "ss_tanimoto_featurize_bits: null fingerprint array");
+    SS_REQUIRE(((reinterpret_cast<uintptr_t>(fa_dev) | reinterpret_cast<uintptr_t>(fb_dev)) & 7) == 0,
+               "ss_tanimoto_featurize_bits: fingerprints must be 8-byte aligned");
+    SS_REQUIRE(X->rows == na && X->cols == nb, "ss_tanimoto_featurize_bits: X must be na x nb");
+    SS_TRY(tanimoto_bits_featurize(ctx, static_cast<const uint64_t*>(fa_dev), na, static_cast<const uint64_t*>(fb_dev), nb, words,
+                                   alpha, weighted != 0, X));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
 int32_t ss_csr_info(const ss_csr* c, int64_t* rows, int64_t* cols, int64_t* nnz, int32_t* has_values) {
     SS_REQUIRE(c, "ss_csr_info: null csr");
     if (rows) *rows = c->rows;

@@ -286,6 +286,36 @@ def featurize_(X: NamedArray, alpha, weighted: bool = True) -> None:
 # ------------------------------------------------------------------------------------------------
 
 
+def jaccard_featurize(D: NamedArray, rows: Sequence[str], cols: Sequence[str], alpha, weighted: bool = True) -> NamedArray:
+    """`featurize(S[rows, cols], alpha, weighted)` with `S = 1 .- pairwise(Jaccard(), D, dims=1)` (the
+    tutorial's similarity step, docs/src/tutorial/fishers-flowers.jl:66, then src/core.jl:106-112) in one
+    kernel: `D` holds one descriptor row per entity, the similarity matrix is never materialised."""
+    ctx = Context.default()
+    ri = D.index_of(rows, 1)
+    ci = D.index_of(cols, 1)
+    da = DMat.from_host(ctx, D.array[ri, :])
+    db = DMat.from_host(ctx, D.array[ci, :])
+    X = DMat(ctx, len(ri), len(ci))
+    check(lib().ss_jaccard_featurize(ctx.h, da.h, db.h, float(alpha), int(bool(weighted)), X.h))
+    return NamedArray(X.to_host(), (list(rows), ["f" + str(c) for c in cols]))
+
+
+def tanimoto_featurize_bits(FA, FB, alpha, weighted: bool = True) -> np.ndarray:
+    """Same for bit-packed fingerprints (uint64 words, one row per entity): X[i,j] = cutoff(|a&b| / |a|b|)."""
+    import torch  # device buffers only
+    ctx = Context.default()
+    FA = np.ascontiguousarray(FA, dtype=np.uint64)
+    FB = np.ascontiguousarray(FB, dtype=np.uint64)
+    assert FA.ndim == 2 and FB.ndim == 2 and FA.shape[1] == FB.shape[1], "fingerprints must have the same number of words"
+    dev = torch.device("cuda", ctx.device)
+    ta = torch.from_numpy(FA.view(np.int64)).to(dev)
+    tb = torch.from_numpy(FB.view(np.int64)).to(dev)
+    X = DMat(ctx, FA.shape[0], FB.shape[0])
+    check(lib().ss_tanimoto_featurize_bits(ctx.h, C.c_void_p(ta.data_ptr()), FA.shape[0], C.c_void_p(tb.data_ptr()),
+                                           FB.shape[0], FA.shape[1], float(alpha), int(bool(weighted)), X.h))
+    return X.to_host()
+
+
 def split(y: NamedArray, k_: int, seed: int = 1) -> List[List[str]]:
     """reference src/core.jl:11-25: shuffle the source names, element i (1-based) -> fold
     `mod(i, k) + 1`.  The shuffle uses NumPy's MT19937 stream, not Julia's MersenneTwister stream
@@ -723,14 +753,22 @@ def _fold_indices(X: NamedArray, y: NamedArray, queries: Sequence[str]):
 
 
 def cross_validate(DT: NamedArray, DD: NamedArray, alpha: float, weighted: bool = True, k_: int = 10,
-                   seed: int = 1, L: int = 20, folds: Optional[List[List[str]]] = None) -> dict:
+                   seed: int = 1, L: int = 20, folds: Optional[List[List[str]]] = None, rank: int = 0,
+                   world: int = 1) -> dict:
     """k-fold de-novo cross-validation: `split` -> `featurize` -> per fold `construct`, `predict`,
     `clean!` -> AuROC / AuPRC over all (query, target) pairs and mean recall@L / precision@L per
-    query.  Returns the predictions with rows in fold order."""
+    query.  Returns the predictions with rows in fold order.
+
+    Folds are independent (SURVEY 8e, outer level): with `world` > 1 rank r evaluates folds[r::world] only and
+    returns {"folds", "yhat", "y"} for those folds (no metrics); `merge_cross_validation` joins the parts
+    gathered on the host and computes the metrics over all folds."""
     ctx = Context.default()
     assert DT.size(1) == DD.size(1), "Labels and features have different number of source nodes"
     if folds is None:
         folds = split(DT, k_, seed=seed)
+    all_folds = folds
+    if world > 1:
+        folds = [f for i, f in enumerate(all_folds) if i % world == rank]
     order = [q for f in folds for q in f]
     N, nt = DT.size(1), DT.size(2)
     dX = DMat.from_host(ctx, DD.array)
@@ -757,15 +795,49 @@ def cross_validate(DT: NamedArray, DD: NamedArray, alpha: float, weighted: bool 
     perm = DIVec.from_host(ctx, DT.index_of(order, 1))
     Yall = DMat(ctx, len(order), nt)
     check(lib().ss_gather(ctx.h, dy.h, perm.h, None, Yall.h))
+    if world > 1:  # partial result: metrics need every fold (merge_cross_validation)
+        return {"folds": folds, "fold_ids": list(range(rank, len(all_folds), world)),
+                "yhat": NamedArray(Rall.to_host(), (order, DT.names(2))),
+                "y": NamedArray(Yall.to_host(), (order, DT.names(2)))}
+    res = {"folds": folds}
+    res.update(_cv_metrics(ctx, Yall, Rall, nt, L))
+    res["yhat"] = NamedArray(Rall.to_host(), (order, DT.names(2)))
+    res["y"] = NamedArray(Yall.to_host(), (order, DT.names(2)))
+    return res
+
+
+def _cv_metrics(ctx, Yall: "DMat", Rall: "DMat", nt: int, L: int) -> dict:
     auc = (C.c_double * 2)()
     check(lib().ss_auroc_auprc_mat(ctx.h, Yall.h, Rall.h, auc))
-    res = {"folds": folds, "AuROC": float(auc[0]), "AuPRC": float(auc[1])}
+    res = {"AuROC": float(auc[0]), "AuPRC": float(auc[1])}
     if nt > L:
         atl = (C.c_double * 2)()
         check(lib().ss_atl(ctx.h, Yall.h, Rall.h, int(L), atl))
         res["recallatL"], res["precisionatL"] = float(atl[0]), float(atl[1])
-    res["yhat"] = NamedArray(Rall.to_host(), (order, DT.names(2)))
-    res["y"] = NamedArray(Yall.to_host(), (order, DT.names(2)))
+    return res
+
+
+def merge_cross_validation(parts: Sequence[dict], L: int = 20) -> dict:
+    """Joins the per-rank results of `cross_validate(..., rank=r, world=n)` (gathered on the host, e.g. with
+    `torch.distributed.all_gather_object`) back into fold order and computes the metrics of the whole
+    cross-validation on the device, exactly as the single-GPU call does."""
+    ctx = Context.default()
+    by_fold = {}
+    for part in parts:
+        off = 0
+        for fid, names in zip(part["fold_ids"], part["folds"]):
+            by_fold[fid] = (names, part["yhat"].array[off:off + len(names)], part["y"].array[off:off + len(names)])
+            off += len(names)
+    ids = sorted(by_fold)
+    folds = [by_fold[i][0] for i in ids]
+    order = [q for f in folds for q in f]
+    cols = parts[0]["yhat"].names(2)
+    yhat = np.concatenate([by_fold[i][1] for i in ids], axis=0) if ids else np.zeros((0, len(cols)))
+    y = np.concatenate([by_fold[i][2] for i in ids], axis=0) if ids else np.zeros((0, len(cols)))
+    res = {"folds": folds}
+    res.update(_cv_metrics(ctx, DMat.from_host(ctx, y), DMat.from_host(ctx, yhat), len(cols), L))
+    res["yhat"] = NamedArray(yhat, (order, cols))
+    res["y"] = NamedArray(y, (order, cols))
     return res
 
 

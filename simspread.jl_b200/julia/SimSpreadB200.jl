@@ -16,7 +16,7 @@ using Random
 
 export cutoff, cutoff!, featurize, featurize!, k, construct, spread, predict, clean!,
     AuROC, AuPRC, BEDROC, recallatL, precisionatL, validity_ratio,
-    maxperformance, meanperformance, meanstdperformance
+    maxperformance, meanperformance, meanstdperformance, jaccard_featurize
 
 const libss = get(ENV, "SIMSPREAD_B200_LIB",
     joinpath(@__DIR__, "..", "lib", "libsimspread_b200.so"))
@@ -142,6 +142,20 @@ function featurize(X::NamedArray, α::AbstractFloat, weighted::Bool=true)
     X′.array = _cutoff(Matrix{Float64}(X.array), Float64(α), weighted)
     setnames!(X′, ["f$f" for f in names(X′, 2)], 2)
     return X′
+end
+
+# `featurize(NamedArray(1 .- pairwise(Jaccard(), D, dims=1))[rows, cols], α, weighted)` of the tutorial
+# (docs/src/tutorial/fishers-flowers.jl:66, 97-99) in one kernel: D holds one descriptor row per entity and
+# the N x N similarity matrix is never materialised (ss_jaccard_featurize).
+function jaccard_featurize(D::NamedMatrix, rows::AbstractVector, cols::AbstractVector, α::AbstractFloat,
+    weighted::Bool=true)
+    da = DMat(Matrix{Float64}(D[rows, :].array))
+    db = DMat(Matrix{Float64}(D[cols, :].array))
+    X = DMat(length(rows), length(cols))
+    check(ccall((:ss_jaccard_featurize, libss), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Cint, Ptr{Cvoid}),
+        ctx().h, da.h, db.h, Float64(α), Cint(weighted), X.h))
+    return NamedArray(Matrix(X), (string.(rows), ["f$c" for c in cols]))
 end
 
 function featurize!(X::NamedArray, α::AbstractFloat, weighted::Bool=true)

@@ -23,5 +23,5 @@ def kats():
 def iris():
     import numpy as np
     d = np.load(os.path.join(ROOT, "tests", "golden", "iris.npz"))
-    return {"S": d["S"], "C": d["C"], "names": [str(x) for x in d["names"]],
+    return {"S": d["S"], "C": d["C"], "F": d["F"], "names": [str(x) for x in d["names"]],
             "classes": [str(x) for x in d["classes"]]}

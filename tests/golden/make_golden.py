@@ -6,7 +6,7 @@ not exist on the GPU box, so tests only ever read the generated files.
 * reference_kats.json : the known-answer vectors of the reference's own test-suite
   (test/runtests.jl line numbers are recorded per entry) and the byte-exact `save` fixtures
   test/data/save1..4.
-* iris.npz : the tutorial data docs/src/tutorial/data/iris.{simmat,classes} (150x150 similarity,
+* iris.npz : the tutorial data docs/src/tutorial/data/iris.{simmat,classes,features} (150x150 similarity,
   150x3 one-hot labels) as arrays + names.  No expected outputs are stored in the reference for
   it; it is used as an extra CUDA-vs-oracle input.
 """
@@ -109,9 +109,10 @@ def main():
 
     S, srows, scols = read_named(f"{REF}/docs/src/tutorial/data/iris.simmat")
     C, crows, ccols = read_named(f"{REF}/docs/src/tutorial/data/iris.classes")
-    assert srows == crows and S.shape == (150, 150) and C.shape == (150, 3)
-    np.savez_compressed(os.path.join(HERE, "iris.npz"), S=S, C=C, names=np.array(srows),
-                        classes=np.array(ccols))
+    F, frows, fcols = read_named(f"{REF}/docs/src/tutorial/data/iris.features")
+    assert srows == crows == frows and S.shape == (150, 150) and C.shape == (150, 3) and F.shape == (150, 4)
+    np.savez_compressed(os.path.join(HERE, "iris.npz"), S=S, C=C, F=F, names=np.array(srows),
+                        classes=np.array(ccols), descriptors=np.array(fcols))
     print("wrote", os.listdir(HERE))
 
 

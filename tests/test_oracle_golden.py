@@ -209,3 +209,27 @@ def test_iris_fixture_runs(iris):
     blk = o.predict_blocks_query(X[np.ix_(qi, si)], X[np.ix_(si, si)], C[si])
     np.testing.assert_allclose(blk, yhat, rtol=1e-13, atol=1e-300)
     assert 0.9 < o.AuROC(C[qi].ravel() > 0, yhat.ravel()) <= 1.0
+
+
+def test_jaccard_similarity_pinned_by_iris_simmat(iris):
+    """the tutorial's `1 .- pairwise(Jaccard(), X, dims=1)` (docs/src/tutorial/fishers-flowers.jl:66).
+    docs/src/tutorial/data/iris.simmat is that matrix for iris.features: the restatement reproduces all
+    22 500 shipped values bit for bit."""
+    S = o.jaccard_similarity(iris["F"], iris["F"])
+    assert S.shape == (150, 150)
+    assert np.array_equal(S, iris["S"])
+    assert np.array_equal(np.diag(S), np.ones(150))
+    assert o.jaccard_similarity(np.zeros((1, 3)), np.zeros((2, 3))).tolist() == [[1.0, 1.0]]  # 0/0: distance 0
+
+
+def test_tanimoto_bits_matches_jaccard_of_indicator_vectors():
+    rng = np.random.default_rng(3)
+    FA = rng.integers(0, 2**63, size=(7, 3), dtype=np.uint64) & rng.integers(0, 2**63, size=(7, 3), dtype=np.uint64)
+    FB = rng.integers(0, 2**63, size=(5, 3), dtype=np.uint64)
+    FA[2] = 0
+    FB[1] = 0
+    T = o.tanimoto_bits(FA, FB)
+    ba = np.unpackbits(FA.view(np.uint8), axis=1).astype(float)
+    bb = np.unpackbits(FB.view(np.uint8), axis=1).astype(float)
+    J = o.jaccard_similarity(ba, bb)
+    assert np.allclose(T, J, rtol=0, atol=2.3e-16) and T[2, 1] == 1.0  # J goes through 1 - (1 - q)
