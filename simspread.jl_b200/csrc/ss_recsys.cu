@@ -18,6 +18,7 @@
 // Work unit: one partial product; algorithmic bytes: 4 B (column index) per partial product, or
 // 12 B for a weighted graph.
 #include <cooperative_groups.h>
+#include <limits.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -252,6 +253,13 @@ struct FusedParams {
     int32_t* redo_list;
 };
 
+// order-preserving image of the high word of a double under Julia's isless (sign-magnitude -> two's complement;
+// -0.0 < +0.0, +NaN above +Inf)
+__device__ __forceinline__ int hi_image(double v) {
+    const int hi = __double2hiint(v);
+    return hi ^ ((hi >> 31) & 0x7fffffff);
+}
+
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -275,8 +283,8 @@ __global__ void __launch_bounds__(FU_TPB, 1024 / FU_TPB) rec_fused_kernel(const 
     __shared__ int32_t s_u1[FU_MAXI];
     __shared__ double s_a[FU_MAXI];
     __shared__ int32_t s_wsum[32];
-    __shared__ uint64_t s_wmax[FU_NW];
-    __shared__ uint64_t s_tau;
+    __shared__ int s_wmax[FU_NW];
+    __shared__ int s_tau;
     __shared__ uint64_t s_ckey[FU_CAP];  // candidate list: used in CTA 0 only, written by the whole cluster
     __shared__ int32_t s_ccol[FU_CAP];
     __shared__ int s_ccnt;
@@ -397,57 +405,59 @@ __global__ void __launch_bounds__(FU_TPB, 1024 / FU_TPB) rec_fused_kernel(const 
         cluster.sync();  // all partial products of this source are in the accumulator row
 
         // ---------------- select ----------------
-        // thread maximum of its interleaved columns: DMNMX + a NaN flag (a NaN sorts above everything, as in isless)
-        double vmax = -INFINITY;
-        bool seen = false, nan = false;
-#pragma unroll 8
-        for (int64_t pi = int64_t(cta) * FU_TPB + tid; pi < npairs; pi += int64_t(FU_C) * FU_TPB) {
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(acc) + pi);
-            const int64_t c = pi << 1;
-            if (c + 1 < r.nt) {
-                vmax = fmax(vmax, fmax(v.x, v.y));
-                nan |= (v.x != v.x) | (v.y != v.y);
-                seen = true;
-            } else if (c < r.nt) {
-                vmax = fmax(vmax, v.x);
-                nan |= (v.x != v.x);
-                seen = true;
+        // The threshold works on the order-preserving image of the HIGH word of a score (sign, exponent, 20
+        // mantissa bits; 3 integer instructions per column): tau = L-th largest warp maximum is a lower bound of
+        // the L-th best score, and every entry whose image reaches tau is a candidate (ranked below by its full key).
+        const double2* accp = reinterpret_cast<const double2*>(acc);
+        const int64_t stride = int64_t(FU_C) * FU_TPB;
+        const int64_t nfull = r.nt >> 1;  // column pairs entirely inside the row
+        int hmax = INT_MIN;
+        {
+            int64_t pi = int64_t(cta) * FU_TPB + tid;
+            for (; pi + 3 * stride < nfull; pi += 4 * stride) {  // 4 independent 128-bit loads in flight per thread
+                const double2 v0 = __ldcg(accp + pi), v1 = __ldcg(accp + pi + stride);
+                const double2 v2 = __ldcg(accp + pi + 2 * stride), v3 = __ldcg(accp + pi + 3 * stride);
+                hmax = max(hmax, max(max(hi_image(v0.x), hi_image(v0.y)), max(hi_image(v1.x), hi_image(v1.y))));
+                hmax = max(hmax, max(max(hi_image(v2.x), hi_image(v2.y)), max(hi_image(v3.x), hi_image(v3.y))));
             }
+            for (; pi < nfull; pi += stride) {
+                const double2 v = __ldcg(accp + pi);
+                hmax = max(hmax, max(hi_image(v.x), hi_image(v.y)));
+            }
+            if ((r.nt & 1) && pi == nfull) hmax = max(hmax, hi_image(__ldcg(acc + r.nt - 1)));  // last, odd column
         }
-        // -0.0 and +0.0 compare equal in fmax: take the lower key so that no entry >= tau can be missed
-        const uint64_t tmax = !seen ? 0 : nan ? 0xFFFFFFFFFFFFFFFFull : rk_isless_key(vmax == 0.0 ? -0.0 : vmax);
-        const uint64_t wm = warp_max_u64(tmax);
+        const int wm = __reduce_max_sync(0xffffffffu, hmax);
         if (lane < FU_C) *cluster.map_shared_rank(&s_wmax[cta * FU_WARPS + warp], lane) = wm;
         cluster.sync();
         if (tid < FU_NW) {  // tau = L-th largest warp maximum (rank by counting; ties broken by position)
-            const uint64_t my = s_wmax[tid];
+            const int my = s_wmax[tid];
             int rank = 0;
+#pragma unroll 8
             for (int j = 0; j < FU_NW; ++j) {
-                const uint64_t o = s_wmax[j];
+                const int o = s_wmax[j];
                 rank += (o > my || (o == my && j < tid)) ? 1 : 0;
             }
             if (rank == L - 1) s_tau = my;
         }
         __syncthreads();
-        const uint64_t tau = s_tau;
+        const int tau = s_tau;
         // rare: a thread whose maximum reaches tau holds candidates; the warp re-reads that thread's columns
         // together (one load round per such thread) and appends every entry >= tau to CTA 0's list
-        unsigned hot = __ballot_sync(0xffffffffu, tmax != 0 && tmax >= tau);
+        unsigned hot = __ballot_sync(0xffffffffu, hmax != INT_MIN && hmax >= tau);
         while (hot) {
             const int src = __ffs(hot) - 1;
             hot &= hot - 1;
             const int64_t first = int64_t(cta) * FU_TPB + (warp << 5) + src;
-            for (int64_t pi = first + int64_t(lane) * (FU_C * FU_TPB); pi < npairs; pi += int64_t(32) * FU_C * FU_TPB) {
-                const double2 v = __ldcg(reinterpret_cast<const double2*>(acc) + pi);
+            for (int64_t pi = first + int64_t(lane) * stride; pi <= nfull; pi += 32 * stride) {
                 const int64_t c = pi << 1;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (c + h >= r.nt) continue;
-                    const uint64_t k = rk_isless_key(h ? v.y : v.x);
-                    if (k >= tau) {
+                    const double v = __ldcg(acc + c + h);
+                    if (hi_image(v) >= tau) {
                         const int pos = atomicAdd(ccnt0, 1);
                         if (pos < FU_CAP) {
-                            ckey0[pos] = k;
+                            ckey0[pos] = rk_isless_key(v);
                             ccol0[pos] = int32_t(c + h);
                         }
                     }

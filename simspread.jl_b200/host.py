@@ -842,33 +842,50 @@ def merge_cross_validation(parts: Sequence[dict], L: int = 20) -> dict:
 
 
 def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: Sequence[float],
-                weighted: bool = True, L: int = 20, rank: int = 0, world: int = 1) -> List[dict]:
+                weighted: bool = True, L: int = 20, rank: int = 0, world: int = 1, layout: str = "auto") -> List[dict]:
     """SimSpread's alpha sweep (BASELINE config 3): for every cutoff alpha, featurize -> construct
     -> predict -> clean! -> metrics on the same query set.  alpha points are independent, so with
-    `world` > 1 rank r evaluates alphas[r::world] (no communication)."""
+    `world` > 1 rank r evaluates alphas[r::world] (no communication).
+
+    The raw similarity blocks S[queries, features] and S[sources, features] are extracted once; per alpha
+    they are thresholded either into dense feature blocks (DMMA chain) or straight into CSR (row-split
+    sparse chain) -- `layout="auto"` picks the sparse chain below SPARSE_DENSITY_THRESHOLD, as `predict`."""
+    assert layout in ("auto", "dense", "sparse")
     ctx = Context.default()
     queries = [str(q) for q in queries]
     dS = DMat.from_host(ctx, DD.array)
-    dX = DMat(ctx, DD.size(1), DD.size(2))
     dy = DMat.from_host(ctx, DT.array)
     Xn = _names_only(DD.names(1), ["f" + c for c in DD.names(2)])
     qi, si, fi, ysi, yqi = _fold_indices(Xn, DT, queries)
     nt = DT.size(2)
     dqi, dsi, dfi, dysi, dyqi = (DIVec.from_host(ctx, a) for a in (qi, si, fi, ysi, yqi))
+    Sq, Ss = DMat(ctx, len(qi), len(fi)), DMat(ctx, len(si), len(fi))  # raw similarities of the two blocks
+    check(lib().ss_gather(ctx.h, dS.h, dqi.h, dfi.h, Sq.h))
+    check(lib().ss_gather(ctx.h, dS.h, dsi.h, dfi.h, Ss.h))
+    del dS
     Xq, Xs = DMat(ctx, len(qi), len(fi)), DMat(ctx, len(si), len(fi))
     Y, Yq, R = DMat(ctx, len(si), nt), DMat(ctx, len(qi), nt), DMat(ctx, len(qi), nt)
     check(lib().ss_gather(ctx.h, dy.h, dysi.h, None, Y.h))
     check(lib().ss_gather(ctx.h, dy.h, dyqi.h, None, Yq.h))
     kq = DIVec(ctx, len(qi))
+    w = int(bool(weighted))
     out = []
     for a in list(alphas)[rank::world]:
-        check(lib().ss_featurize(ctx.h, dS.h, float(a), int(bool(weighted)), dX.h))
-        check(lib().ss_gather(ctx.h, dX.h, dqi.h, dfi.h, Xq.h))
-        check(lib().ss_gather(ctx.h, dX.h, dsi.h, dfi.h, Xs.h))
-        check(lib().ss_predict_query(ctx.h, Xq.h, Xs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
+        use_sparse = False
+        if layout != "dense" and len(qi) and len(si) and len(fi):
+            cq = DCsr.from_dense(ctx, Sq, float(a), bool(weighted))
+            if layout == "sparse" or cq.density < SPARSE_DENSITY_THRESHOLD:
+                cs = DCsr.from_dense(ctx, Ss, float(a), bool(weighted), by_columns=True)
+                use_sparse = layout == "sparse" or cs.density < SPARSE_DENSITY_THRESHOLD
+        if use_sparse:
+            check(lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
+        else:
+            check(lib().ss_featurize(ctx.h, Sq.h, float(a), w, Xq.h))
+            check(lib().ss_featurize(ctx.h, Ss.h, float(a), w, Xs.h))
+            check(lib().ss_predict_query(ctx.h, Xq.h, Xs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
         auc, atl = (C.c_double * 2)(), (C.c_double * 2)()
         check(lib().ss_auroc_auprc_mat(ctx.h, Yq.h, R.h, auc))
-        rec = {"alpha": float(a), "AuROC": float(auc[0]), "AuPRC": float(auc[1])}
+        rec = {"alpha": float(a), "AuROC": float(auc[0]), "AuPRC": float(auc[1]), "layout": "sparse" if use_sparse else "dense"}
         if nt > L:
             check(lib().ss_atl(ctx.h, Yq.h, R.h, int(L), atl))
             rec["recallatL"], rec["precisionatL"] = float(atl[0]), float(atl[1])
