@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(256)
 // A source whose candidate list overflows (massive ties, e.g. an all-zero row) is put on a redo list
 // and goes through the group kernels above.
 constexpr int FU_CAP = 2048;            // candidate capacity
-constexpr int FU_UNIT = 16;             // co-raters per work unit (finer units -> shorter tail at the barrier)
 
 struct FusedParams {
     RecParams r;          // r.acc: [clusters][ldacc]
@@ -271,7 +270,7 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 
 // FU_C CTAs per cluster (launch attribute), FU_TPB threads per CTA, 1024 / FU_TPB CTAs per SM: with two
 // CTAs of different clusters on one SM the select / zero phases of one source overlap the RED stream of another.
-template <bool WEIGHTED, int FU_C, int FU_TPB>
+template <bool WEIGHTED, int FU_C, int FU_TPB, int FU_UNIT>  // FU_UNIT: co-raters per work unit
 __global__ void __launch_bounds__(FU_TPB, 1024 / FU_TPB) rec_fused_kernel(const FusedParams p) {
     constexpr int FU_WARPS = FU_TPB / 32;
     constexpr int FU_NW = FU_C * FU_WARPS;  // warp maxima per source
@@ -582,9 +581,9 @@ int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-template <bool WEIGHTED, int FU_C, int FU_TPB>
+template <bool WEIGHTED, int FU_C, int FU_TPB, int FU_UNIT>
 int32_t launch_fused(ss_ctx* ctx, FusedParams& fp, int64_t ldacc, int64_t nsrc, int* ncl_out) {
-    auto kern = rec_fused_kernel<WEIGHTED, FU_C, FU_TPB>;
+    auto kern = rec_fused_kernel<WEIGHTED, FU_C, FU_TPB, FU_UNIT>;
     if (FU_C > 8) SS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -671,17 +670,19 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
     // 120 SMs co-resident on B200); "16x512" = 16 CTAs of 512 threads, two CTAs per SM (non-portable size; 14
     // clusters on B200, measured 3 % slower: the kernel is bound by the RED issue rate of the SMs it covers)
     const char* shape = getenv("SS_RECSYS_SHAPE");
-    const bool big = shape && !strcmp(shape, "16x512");
+    const int unit = env_int("SS_RECSYS_UNIT", 16);
+    const int64_t nsrc = s_end - s_begin;
     int ncl = 0;
     int32_t st;
-    if (big)
-        st = weighted ? launch_fused<true, 16, 512>(ctx, fp, ldacc, s_end - s_begin, &ncl)
-                      : launch_fused<false, 16, 512>(ctx, fp, ldacc, s_end - s_begin, &ncl);
-    else
-        st = weighted ? launch_fused<true, 8, 1024>(ctx, fp, ldacc, s_end - s_begin, &ncl)
-                      : launch_fused<false, 8, 1024>(ctx, fp, ldacc, s_end - s_begin, &ncl);
+#define SS_FUSED(C_, T_, U_) (weighted ? launch_fused<true, C_, T_, U_>(ctx, fp, ldacc, nsrc, &ncl) : launch_fused<false, C_, T_, U_>(ctx, fp, ldacc, nsrc, &ncl))
+    if (shape && !strcmp(shape, "16x512")) st = SS_FUSED(16, 512, 16);
+    else if (shape && !strcmp(shape, "8x512")) st = SS_FUSED(8, 512, 16);
+    else if (unit == 8) st = SS_FUSED(8, 1024, 8);
+    else st = SS_FUSED(8, 1024, 16);
+#undef SS_FUSED
+    const bool big = shape && strcmp(shape, "8x1024");
     SS_TRY(st);
-    if (env_int("SS_RECSYS_VERBOSE", 0)) fprintf(stderr, "ss_recommend_topl: %d clusters (%s)\n", ncl, big ? "16x512" : "8x1024");
+    if (env_int("SS_RECSYS_VERBOSE", 0)) fprintf(stderr, "ss_recommend_topl: %d clusters (%s, unit %d)\n", ncl, big ? shape : "8x1024", unit);
     int32_t redo = 0;  // sources whose candidate list overflowed take the three-kernel form
     SS_CHECK_CUDA(cudaMemcpyAsync(&redo, fp.redo_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -215,3 +215,51 @@ class LibBackend:
             return
         self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_N, self.mXq.h, self.mT.h, self.mR.h, None,
                                       self.vkt.h if clean else None))
+
+
+def global_auroc_auprc(ss, ctx, torch, dist, y_local, r_local, world: int, rank: int):
+    """AuROC / AuPRC over the scores of ALL ranks (reference src/performance.jl:49-63, 74-89 on the
+    concatenation of the per-rank (label, score) lists -- both areas are order-independent).
+
+    Exchange step: the per-rank score slabs (float64) and labels (uint8) are gathered on rank 0 with one NCCL
+    gather each (padded to the largest slab), and rank 0 runs the device sort + scan (`ss_auroc_auprc`) on the
+    concatenation; the result is broadcast.  Needs 9 B per score plus the 18 B per score of sort buffers on rank
+    0 (C4 on 8 GPUs: 45 GB + 90 GB of 180 GB).  A sample-sort over the ranks would remove that limit; per-query
+    metrics (recall@L / precision@L) need no exchange at all."""
+    from ._lib import check
+    dev = r_local.device
+    scores = r_local.reshape(-1).to(torch.float64)
+    labels = (y_local.reshape(-1) != 0).to(torch.uint8)
+    assert scores.numel() == labels.numel(), "The number of scores must be equal to the number of labels"
+    n = torch.tensor([scores.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(sizes, n)
+    else:
+        sizes = [n]
+    sizes = [int(s.item()) for s in sizes]
+    out = torch.zeros(2, dtype=torch.float64, device=dev)
+    if world == 1:
+        all_s, all_l = scores, labels
+    else:
+        cap = max(sizes)
+        ps = torch.zeros(cap, dtype=torch.float64, device=dev)
+        pl = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        ps[:scores.numel()] = scores
+        pl[:labels.numel()] = labels
+        gs = [torch.empty(cap, dtype=torch.float64, device=dev) for _ in range(world)] if rank == 0 else None
+        gl = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(ps, gs, dst=0)
+        dist.gather(pl, gl, dst=0)
+        if rank == 0:
+            all_s = torch.cat([g[:m] for g, m in zip(gs, sizes)])
+            all_l = torch.cat([g[:m] for g, m in zip(gl, sizes)])
+    if rank == 0:
+        res = (C.c_double * 2)()
+        torch.cuda.synchronize(dev)
+        check(ss.lib().ss_auroc_auprc(ctx.h, C.c_void_p(all_l.data_ptr()), C.c_void_p(all_s.data_ptr()),
+                                      int(all_s.numel()), res))
+        out[0], out[1] = float(res[0]), float(res[1])
+    if world > 1:
+        dist.broadcast(out, src=0)
+    return float(out[0].item()), float(out[1].item())

@@ -24,6 +24,7 @@ ap.add_argument("--c5-items", type=int, default=500_000)
 ap.add_argument("--c5-frac", type=float, default=1.0)
 ap.add_argument("--skip-c3", action="store_true")
 ap.add_argument("--skip-c5", action="store_true")
+ap.add_argument("--skip-auc", action="store_true")
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", 0))
@@ -164,6 +165,42 @@ if not args.skip_c5:
         "spot_check_max_rel_err_top20": worst}
     if rank == 0:
         print(json.dumps(out["C5_sparse_recommender"]), flush=True)
+
+# ---------------------------------------------------------------- global AuROC / AuPRC over row-sharded scores
+if not args.skip_auc:
+    from simspread_b200.sharded import global_auroc_auprc
+    m = 50_000_000 + 1000 * rank  # ragged slabs
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777 + rank)
+    sc = torch.rand(m, dtype=torch.float64, device=dev, generator=gen)
+    sc = torch.round(sc * 1e6) / 1e6  # ties across ranks
+    lb = (torch.rand(m, device=dev, generator=gen) < 0.01 + 0.05 * sc).to(torch.float64)
+    global_auroc_auprc(ss, ctx, torch, dist, lb[:1000], sc[:1000], world, rank)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    au = global_auroc_auprc(ss, ctx, torch, dist, lb, sc, world, rank)
+    t = max_over_ranks(time.perf_counter() - t0)
+    ok = None
+    if rank == 0:  # the same slabs regenerated and concatenated on one GPU
+        parts_s, parts_l = [], []
+        for r_ in range(world):
+            g2 = torch.Generator(device=dev)
+            g2.manual_seed(777 + r_)
+            m2 = 50_000_000 + 1000 * r_
+            s2 = torch.round(torch.rand(m2, dtype=torch.float64, device=dev, generator=g2) * 1e6) / 1e6
+            parts_l.append((torch.rand(m2, device=dev, generator=g2) < 0.01 + 0.05 * s2).to(torch.uint8))
+            parts_s.append(s2)
+        S_, L_ = torch.cat(parts_s[::-1]), torch.cat(parts_l[::-1])  # another order: the areas must not change
+        ref = (C.c_double * 2)()
+        torch.cuda.synchronize()
+        check(lib.ss_auroc_auprc(ctx.h, C.c_void_p(L_.data_ptr()), C.c_void_p(S_.data_ptr()), int(S_.numel()), ref))
+        ok = bool(abs(ref[0] - au[0]) <= 1e-12 * abs(ref[0]) and abs(ref[1] - au[1]) <= 1e-12 * abs(ref[1]))
+        out["global_auroc_auprc"] = {"scores_total": int(S_.numel()), "AuROC": au[0], "AuPRC": au[1], "wall_s": t,
+                                     "scores_per_s": S_.numel() / t, "matches_single_gpu_concatenation": ok,
+                                     "exchange": "NCCL gather of score / label slabs to rank 0, device sort + scan there"}
+        print(json.dumps(out["global_auroc_auprc"]), flush=True)
+        assert ok
+    del sc, lb
 
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)

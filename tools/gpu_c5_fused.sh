@@ -1,15 +1,11 @@
 #!/bin/bash
-# fused cluster kernel for config 5: full GPU parity suite, bench at 5 % of the users, ncu of the fused kernel
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_gpu.log
-export SS_RECSYS_VERBOSE=1
+export SS_RECSYS_VERBOSE=1 C5_REPS=4
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 300 python tools/bench_c5.py 2000000 500000 0.05 > gpurun_out/c5_$name.log 2>&1; echo "$name exit $?"; grep "clusters" gpurun_out/c5_$name.log | tail -1; tail -1 gpurun_out/c5_$name.log | cut -c1-330
+  env "$@" timeout 300 python tools/bench_c5.py 2000000 500000 0.05 > gpurun_out/c5_$name.log 2>&1; echo "$name exit $?"; grep "clusters" gpurun_out/c5_$name.log | tail -1; tail -1 gpurun_out/c5_$name.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_all_reps'], d['spot_check_max_rel_err_top20'])"
   cp gpurun_out/c5.json gpurun_out/c5_$name.json
 }
-run 8x1024 SS_RECSYS_SHAPE=8x1024
-run 16x512 SS_RECSYS_SHAPE=16x512
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'rec_fused' -s 1 -c 1 \
-    -o gpurun_out/r01_c5_fused_ncu -f python tools/bench_c5.py 2000000 500000 0.002 > gpurun_out/ncu_c5_fused.log 2>&1
-echo "ncu exit $?"
+run prefetch
+run prefetch_unit8 SS_RECSYS_UNIT=8
+timeout 300 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "recommender" > gpurun_out/pytest_rec.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_rec.log
