@@ -116,6 +116,16 @@ SS_API int32_t ss_ivec_info(const ss_ivec* v, int64_t* n, void** devptr);
 SS_API int32_t ss_ivec_upload(ss_ctx* ctx, ss_ivec* v, const int32_t* host);
 SS_API int32_t ss_ivec_download(ss_ctx* ctx, const ss_ivec* v, int32_t* host);
 
+/* ---- host I/O: read_namedmatrix fast path ---------------------------------------------------------- */
+/* read_namedmatrix [src/utils.jl:50-53: readdlm(filepath, delimiter, String); :30-32 parse.(Float64, block)]
+ * for large matrices: all host cores parse the value block of a delimited text file into a caller-owned
+ * column-major float64 buffer.  Every occurrence of `delimiter` separates two fields (readdlm with an explicit
+ * delimiter), '\n' (optionally preceded by '\r') ends a line.  The host layer reads the names (first line /
+ * first field of each line) itself and applies the reference's sort by name (:38). */
+SS_API int32_t ss_text_matrix_dims(const char* path, int32_t delimiter, int64_t* lines_out, int64_t* fields_out);
+SS_API int32_t ss_text_matrix_read(const char* path, int32_t delimiter, int32_t skip_lines, int32_t skip_fields,
+                                   double* values, int64_t rows, int64_t cols, int64_t ld);
+
 /* ---- (1) featurization ------------------------------------------------------------------- */
 /* cutoff.(S, alpha, weighted)  [src/core.jl:37-43 scalar rule, :55-60 array, :106-112 featurize,
  * :129-132 featurize!]: X[i,j] = S[i,j] >= alpha ? (weighted ? S[i,j] : 1.0) : 0.0 (NaN -> 0).

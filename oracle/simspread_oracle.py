@@ -590,6 +590,38 @@ def meanstdperformance(y, yhat, metric):
 
 
 # --------------------------------------------------------------------------------------------
+# utils.jl
+# --------------------------------------------------------------------------------------------
+
+
+def read_namedmatrix(text: str, delimiter: str = " ", rows: bool = True, cols: bool = True):
+    """`read_namedmatrix(filepath, delimiter, Float64; rows, cols)` (src/utils.jl:50-53) on the contents of a
+    file: `readdlm(filepath, delimiter, String)` splits every line at EVERY delimiter (a leading delimiter
+    yields an empty first cell -- the corner of the header line), `_parse_matrix` (:24-40) takes the value
+    block `M[r_idx:end, c_idx:end]`, the names from the first column / row (or "R#i" / "C#j") and re-orders
+    rows and columns by sorted name (:38).  Returns (values, row_names, col_names)."""
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    M = [ln.rstrip("\r").split(delimiter) for ln in lines]
+    c_idx = 1 if rows else 0
+    r_idx = 1 if cols else 0
+    values = np.array([[float(v) for v in row[c_idx:]] for row in M[r_idx:]], dtype=np.float64)
+    if values.size == 0:
+        values = values.reshape(len(M) - r_idx, max(0, (len(M[0]) if M else 0) - c_idx))
+    row_names = [row[0] for row in M[r_idx:]] if rows else [f"R#{i + 1}" for i in range(values.shape[0])]
+    col_names = list(M[0][c_idx:]) if cols else [f"C#{j + 1}" for j in range(values.shape[1])]
+    ro = sorted(range(len(row_names)), key=lambda i: row_names[i])
+    co = sorted(range(len(col_names)), key=lambda j: col_names[j])
+    return values[np.ix_(ro, co)], [row_names[i] for i in ro], [col_names[j] for j in co]
+
+
+def namedmatrix2matrix(values, row_names, col_names) -> List[List[object]]:
+    """`_namedmatrix2matrix` (src/utils.jl:6): `vcat(["" names(M, 2)...], hcat(names(M, 1), M))`."""
+    return [[""] + list(col_names)] + [[r] + list(values[i]) for i, r in enumerate(row_names)]
+
+
+# --------------------------------------------------------------------------------------------
 # upstream similarity (not in src/: the tutorial's user-side step, docs/src/tutorial/fishers-flowers.jl:66)
 # --------------------------------------------------------------------------------------------
 

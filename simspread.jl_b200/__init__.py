@@ -12,8 +12,8 @@ from ._lib import SimSpreadError, header_symbols, lib  # noqa: F401
 from .namedarray import NamedArray  # noqa: F401
 from .host import (  # noqa: F401
     AuPRC, AuROC, BEDROC, Context, alpha_sweep, cross_validate, DCsr, DIVec, DMat, Graph, accuracy, balancedaccuracy, clean_, construct, cutoff,
-    cutoff_, f1score, featurize, featurize_, jaccard_featurize, tanimoto_featurize_bits, k, mcc, maxperformance, merge_cross_validation, meanperformance, meanstdperformance, precision, precisionatL, predict, recall,
-    recallatL, recommend_topl, save, split, spread, validity_ratio,
+    cutoff_, f1score, featurize, featurize_, jaccard_featurize, tanimoto_featurize_bits, k, mcc, maxperformance, merge_cross_validation, meanperformance, meanstdperformance, precision, precisionatL, predict, read_namedmatrix, recall,
+    recallatL, recommend_topl, save, split, spread, validity_ratio, writedlm,
 )
 from ._build import build, lib_path  # noqa: F401
 

@@ -842,7 +842,8 @@ def merge_cross_validation(parts: Sequence[dict], L: int = 20) -> dict:
 
 
 def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: Sequence[float],
-                weighted: bool = True, L: int = 20, rank: int = 0, world: int = 1, layout: str = "auto") -> List[dict]:
+                weighted: bool = True, L: int = 20, rank: int = 0, world: int = 1, layout: str = "auto",
+                timing: Optional[dict] = None) -> List[dict]:
     """SimSpread's alpha sweep (BASELINE config 3): for every cutoff alpha, featurize -> construct
     -> predict -> clean! -> metrics on the same query set.  alpha points are independent, so with
     `world` > 1 rank r evaluates alphas[r::world] (no communication).
@@ -851,7 +852,9 @@ def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: 
     they are thresholded either into dense feature blocks (DMMA chain) or straight into CSR (row-split
     sparse chain) -- `layout="auto"` picks the sparse chain below SPARSE_DENSITY_THRESHOLD, as `predict`."""
     assert layout in ("auto", "dense", "sparse")
+    import time as _time
     ctx = Context.default()
+    t_start = _time.perf_counter()
     queries = [str(q) for q in queries]
     dS = DMat.from_host(ctx, DD.array)
     dy = DMat.from_host(ctx, DT.array)
@@ -870,6 +873,8 @@ def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: 
     kq = DIVec(ctx, len(qi))
     w = int(bool(weighted))
     out = []
+    ctx.sync()
+    t_setup = _time.perf_counter()
     for a in list(alphas)[rank::world]:
         use_sparse = False
         if layout != "dense" and len(qi) and len(si) and len(fi):
@@ -892,6 +897,9 @@ def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: 
         check(lib().ss_k_rows(ctx.h, R.h, kq.h))
         rec["validity_ratio"] = float(kq.to_host().astype(np.int64).sum() / (len(qi) * nt))
         out.append(rec)
+    if timing is not None:  # setup = upload of S / y + block extraction (once per rank); sweep = the alpha points
+        timing["setup_s"] = t_setup - t_start
+        timing["sweep_s"] = _time.perf_counter() - t_setup
     return out
 
 
@@ -951,7 +959,8 @@ def meanstdperformance(y, yhat, metric) -> Tuple[float, float]:
 
 
 def _jl_string(x) -> str:
-    """Julia `string(x)` for the numbers `save` writes (Int or Float64, shortest round-trip)."""
+    """Julia `string(x)` for the numbers `save` / `writedlm` write (Int or Float64: shortest round-trip digits,
+    fixed notation for decimal exponents -4..5, `d.ddde±x` otherwise -- Base.Ryu.writeshortest)."""
     if isinstance(x, (bool, np.bool_)):
         return "true" if x else "false"
     if isinstance(x, (int, np.integer)):
@@ -961,13 +970,73 @@ def _jl_string(x) -> str:
         return "NaN"
     if x in (float("inf"), float("-inf")):
         return "Inf" if x > 0 else "-Inf"
-    r = repr(x)
-    if "e" in r:
-        mant, exp = r.split("e")
-        if "." not in mant:
-            mant += ".0"
-        return f"{mant}e{int(exp)}"
-    return r
+    if x == 0:
+        return "-0.0" if np.signbit(x) else "0.0"
+    from decimal import Decimal
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digits = "".join(map(str, digits)).rstrip("0") or "0"
+    e10 = len("".join(map(str, Decimal(repr(x)).as_tuple().digits))) + exp - 1  # x = d.ddd * 10^e10
+    neg = "-" if sign else ""
+    if -5 < e10 < 6:
+        if e10 >= 0:
+            ip = (digits + "0" * (e10 + 1))[:e10 + 1]
+            fp = digits[e10 + 1:] or "0"
+        else:
+            ip, fp = "0", "0" * (-e10 - 1) + digits
+        return f"{neg}{ip}.{fp}"
+    return f"{neg}{digits[0]}.{digits[1:] or '0'}e{e10}"
+
+
+def read_namedmatrix(filepath: str, delimiter: str = " ", valuetype=float, rows: bool = True, cols: bool = True) -> NamedArray:
+    """`read_namedmatrix(filepath, delimiter, valuetype; rows, cols)` (reference src/utils.jl:50-53 and
+    `_parse_matrix` :24-40): names from the first row / column (or `R#i` / `C#j`), values parsed as Float64,
+    rows and columns re-ordered by sorted name (:38).  The value block is parsed by the library's
+    multi-threaded host reader (`ss_text_matrix_read`), the names here."""
+    assert len(delimiter) == 1, "delimiter must be a single character"
+    path = os.fspath(filepath).encode()
+    d = ord(delimiter)
+    nl, nf = C.c_int64(), C.c_int64()
+    check(lib().ss_text_matrix_dims(path, d, C.byref(nl), C.byref(nf)))
+    nr, nc = nl.value - int(cols), nf.value - int(rows)
+    if nr < 0 or nc < 0:
+        raise ValueError(f"{filepath}: no value block")
+    vals = np.zeros((nr, nc), order="F")
+    check(lib().ss_text_matrix_read(path, d, int(cols), int(rows), vals.ctypes.data, nr, nc, max(nr, 1)))
+    row_names = [f"R#{i + 1}" for i in range(nr)]
+    col_names = [f"C#{j + 1}" for j in range(nc)]
+    if rows or cols:
+        with open(filepath, "r", newline="") as f:
+            for i, line in enumerate(f):
+                line = line.rstrip("\n").rstrip("\r")
+                if i == 0 and cols:
+                    col_names = line.split(delimiter)[int(rows):]
+                    if not rows:
+                        break
+                    continue
+                if not rows:
+                    break
+                if i - int(cols) < nr:
+                    row_names[i - int(cols)] = line.split(delimiter, 1)[0]
+    if valuetype is not float and valuetype is not np.float64:
+        vals = vals.astype(valuetype)
+    ro = sorted(range(nr), key=lambda i: row_names[i])
+    co = sorted(range(nc), key=lambda j: col_names[j])
+    return NamedArray(vals[np.ix_(ro, co)], ([row_names[i] for i in ro], [col_names[j] for j in co]))
+
+
+def writedlm(io, x: NamedArray, delimiter: str = "\t") -> None:
+    """`writedlm(io, x::NamedMatrix[, delimiter])` (reference src/utils.jl:6-11): the matrix
+    `["" names(x, 2)...; names(x, 1) x]` written with Julia's `print` of each cell."""
+    close = isinstance(io, (str, os.PathLike))
+    f = open(io, "w") if close else io
+    try:
+        f.write(delimiter.join([""] + [str(c) for c in x.names(2)]) + "\n")
+        arr = x.array
+        for i, r in enumerate(x.names(1)):
+            f.write(delimiter.join([str(r)] + [_jl_string(v) for v in arr[i]]) + "\n")
+    finally:
+        if close:
+            f.close()
 
 
 def save(filepath: str, *args, delimiter: str = "\t") -> None:

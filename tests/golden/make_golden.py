@@ -104,6 +104,17 @@ def main():
     for i in (1, 2, 3, 4):
         with open(f"{REF}/test/data/save{i}") as f:
             kats["save"]["files"][f"save{i}"] = f.read()
+    kats["read_namedmatrix"] = {"src": "test/runtests.jl:8-18, test/data/mat1..4", "files": {},
+                                "expect": {"mat1": {"rows": True, "cols": True, "rownames": ["s1", "s2"], "colnames": ["t1", "t2", "t3"]},
+                                           "mat2": {"rows": True, "cols": False, "rownames": ["s1", "s2"], "colnames": ["C#1", "C#2", "C#3"]},
+                                           "mat3": {"rows": False, "cols": True, "rownames": ["R#1", "R#2"], "colnames": ["t1", "t2", "t3"]},
+                                           "mat4": {"rows": False, "cols": False, "rownames": ["R#1", "R#2"], "colnames": ["C#1", "C#2", "C#3"]}},
+                                "values": [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0]]}
+    for i in (1, 2, 3, 4):
+        with open(f"{REF}/test/data/mat{i}") as f:
+            kats["read_namedmatrix"]["files"][f"mat{i}"] = f.read()
+    with open(f"{REF}/docs/src/tutorial/data/iris.classes") as f:
+        kats["read_namedmatrix"]["files"]["iris.classes"] = f.read()
     with open(os.path.join(HERE, "reference_kats.json"), "w") as f:
         json.dump(kats, f, indent=1)
 

@@ -92,3 +92,73 @@ def test_save_matches_reference_fixtures(tmp_path, kats):
         assert p.read_text() == sv["files"][name]
     ss.save(str(tmp_path / "save1"), y, yhat)  # "a+": appends
     assert (tmp_path / "save1").read_text() == sv["files"]["save1"] * 2
+
+
+# ---------------------------------------------------------------------------------------------
+# host I/O (no GPU involved): read_namedmatrix / writedlm, reference src/utils.jl
+# ---------------------------------------------------------------------------------------------
+
+
+def test_read_namedmatrix_reference_fixtures(built, kats, tmp_path):
+    """test/runtests.jl:8-18 on test/data/mat1..4, through the native reader, against the oracle restatement."""
+    from oracle import simspread_oracle as o
+    g = kats["read_namedmatrix"]
+    for name, exp in g["expect"].items():
+        p = tmp_path / name
+        p.write_text(g["files"][name])
+        got = ss.read_namedmatrix(str(p), rows=exp["rows"], cols=exp["cols"])
+        assert np.array_equal(got.array, np.array(g["values"]))
+        assert got.names(1) == exp["rownames"] and got.names(2) == exp["colnames"]
+        v, r, c = o.read_namedmatrix(g["files"][name], " ", exp["rows"], exp["cols"])
+        assert np.array_equal(v, got.array) and r == got.names(1) and c == got.names(2)
+    # the tutorial's label file (docs/src/tutorial/fishers-flowers.jl:12)
+    p = tmp_path / "iris.classes"
+    p.write_text(g["files"]["iris.classes"])
+    got = ss.read_namedmatrix(str(p))
+    v, r, c = o.read_namedmatrix(g["files"]["iris.classes"])
+    assert got.array.shape == (150, 3) and np.array_equal(v, got.array) and r == got.names(1) and c == got.names(2)
+    assert got.array.sum() == 150.0
+
+
+def test_read_namedmatrix_large_random_matches_oracle_bit_for_bit(built, tmp_path):
+    from oracle import simspread_oracle as o
+    rng = np.random.default_rng(5)
+    n, m = 257, 131
+    vals = rng.random((n, m)) * 10.0 ** rng.integers(-12, 12, size=(n, m))
+    vals[0, 0], vals[1, 1], vals[2, 2], vals[3, 3] = np.inf, -np.inf, 0.0, -0.0
+    rn = [f"s{rng.integers(0, 10**6):06d}_{i}" for i in range(n)]  # unsorted names: the reader sorts them
+    cn = [f"t{j}" for j in range(m)]                                # "t10" < "t2": string order
+    text = "\t".join([""] + cn) + "\n" + "".join("\t".join([rn[i]] + [repr(float(x)) for x in vals[i]]) + "\n" for i in range(n))
+    text = text.replace("inf", "Inf")
+    p = tmp_path / "big.tsv"
+    p.write_text(text)
+    got = ss.read_namedmatrix(str(p), "\t")
+    v, r, c = o.read_namedmatrix(text, "\t")
+    assert r == got.names(1) == sorted(rn) and c == got.names(2) == sorted(cn)
+    assert np.array_equal(v.view(np.uint64), got.array.view(np.uint64))  # including the sign of -0.0
+    # CRLF line ends, no trailing newline, '+' signs
+    p2 = tmp_path / "crlf.txt"
+    p2.write_bytes(b" a b\r\nx +1.5 2\r\ny 3e-2 -4")
+    got2 = ss.read_namedmatrix(str(p2))
+    assert got2.array.tolist() == [[1.5, 2.0], [0.03, -4.0]] and got2.names(1) == ["x", "y"] and got2.names(2) == ["a", "b"]
+    # ragged line -> error, not garbage
+    p3 = tmp_path / "ragged.txt"
+    p3.write_text(" a b\nx 1 2\ny 3\n")
+    with pytest.raises(ss.SimSpreadError, match="line 3"):
+        ss.read_namedmatrix(str(p3))
+
+
+def test_writedlm_layout_and_julia_number_format(built, tmp_path):
+    """src/utils.jl:6-11: `["" names(M, 2)...; names(M, 1) M]`, cells printed like Julia prints Float64."""
+    from oracle import simspread_oracle as o
+    from simspread_b200.host import _jl_string
+    X = ss.NamedArray(np.array([[0.0, 1.0, 0.5], [1e-5, 1234567.8, -99.0]]), (["s1", "s2"], ["t1", "t2", "t3"]))
+    p = tmp_path / "out.tsv"
+    ss.writedlm(str(p), X)
+    assert p.read_text() == "\tt1\tt2\tt3\ns1\t0.0\t1.0\t0.5\ns2\t1.0e-5\t1.2345678e6\t-99.0\n"
+    want = o.namedmatrix2matrix(X.array, X.names(1), X.names(2))
+    assert [ln.split("\t") for ln in p.read_text().splitlines()] == [[c if isinstance(c, str) else _jl_string(c) for c in row] for row in want]
+    back = ss.read_namedmatrix(str(p), "\t")
+    assert np.array_equal(back.array, X.array) and back.names(1) == X.names(1) and back.names(2) == X.names(2)
+    for v, s_ in [(100000.0, "100000.0"), (1e6, "1.0e6"), (0.0001, "0.0001"), (0.1 + 0.2, "0.30000000000000004"), (5e-324, "5.0e-324")]:
+        assert _jl_string(v) == s_

@@ -60,5 +60,42 @@ out["C3_alpha_sweep_21_points"] = {"shape": {"nq": nq, "ns": ns, "nt": nt}, "gpu
                                    "note": "dense DMMA chain for every alpha (alpha_sweep gathers dense blocks); "
                                            "the sparse chain is selected by predict(layout='auto')"}
 print(json.dumps({k: v for k, v in out["C3_alpha_sweep_21_points"].items() if k != "points"}), flush=True)
+
+# the reference's own formulation beside it -- (i) the literal CPU path (dense n x n construct ->
+# spread -> A*(W*W), NumPy/OpenBLAS restatement, all host cores) for ONE alpha of C3 (the cost of the dense
+# DGEMMs does not depend on alpha); (ii) torch.matmul in Float32 on the GPU for the padded n x n problem, the
+# proxy for the reference's `GPU=true` cuBLAS SGEMM path (src/core.jl:404-419), at the C2 and C3 sizes.
+if os.environ.get("SS_SKIP_REFERENCE_FORMS") != "1":
+    import torch
+    t0 = time.perf_counter()
+    Xo, xr, xc = o.featurize(S3, n3, n3, 0.5, True)
+    Ao, Bo, nn = o.construct_queries(Y3, (n3, t3), Xo, (xr, xc), n3[:nq])
+    w = o.predict_dense(Ao, Bo, nn, n3[:nq], t3)
+    o.clean(w, Ao, nn, t3)
+    t_cpu3 = time.perf_counter() - t0
+    n_full = Ao.shape[0]
+    del Ao, Bo, Xo
+    out["C3_cpu_literal_one_alpha"] = {"alpha": 0.5, "n": n_full, "wall_s": t_cpu3, "scores_per_s": nq * nt / t_cpu3,
+                                       "cores": os.cpu_count(), "kind": "NumPy/OpenBLAS restatement of the reference CPU path (not Julia)"}
+    print(json.dumps(out["C3_cpu_literal_one_alpha"]), flush=True)
+    proxy = {}
+    for label, n_ in (("C2_fold_n1510", 1510), ("C3_n17000", 17000)):
+        A32 = torch.rand((n_, n_), dtype=torch.float32, device="cuda")
+        W32 = torch.rand((n_, n_), dtype=torch.float32, device="cuda")
+        torch.backends.cuda.matmul.allow_tf32 = False
+        for _ in range(2):
+            F32 = A32 @ (W32 @ W32)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            F32 = A32 @ (W32 @ W32)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1) / 3
+        proxy[label] = {"n": n_, "ms": ms_, "tflops_fp32": 4 * n_ ** 3 / (ms_ * 1e-3) / 1e12}
+        del A32, W32, F32
+    out["reference_gpu_true_proxy_torch_fp32_dense_nxn"] = proxy
+    print(json.dumps(proxy), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
