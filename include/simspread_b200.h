@@ -249,6 +249,23 @@ SS_API int32_t ss_atl(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, int32_t
  * scores: float64, both device pointers.  out[0] = AuROC, out[1] = AuPRC. */
 SS_API int32_t ss_auroc_auprc(ss_ctx* ctx, const void* labels_u8_dev, const void* scores_f64_dev, int64_t M,
                        double* out2);
+/* AuROC / AuPRC of a list spread over several GPUs (one ss_ctx per rank; the exchange itself is done by the host
+ * layer with NCCL, simspread.jl_b200/sharded.py).  Keys are the order-preserving uint64 image of a score under
+ * Julia's isless.  Returned device pointers live in the context's sort buffers until the next metric call.
+ *   ss_auc_sort            (labels, scores) or (labels, keys_in != NULL) -> ascending (key, label) arrays
+ *   ss_auc_lower_bound     pos[q] = #keys < query[q]  (splitter positions; host arrays in / out)
+ *   ss_auc_segment_summary {positives, index of the last run start or -1, positives before it} of a sorted array
+ *   ss_auc_segment_integrate  signed trapezoid sums (ROC, PR) of the thresholds inside this key range, including
+ *       the joint to the range below; global6 = {P, M_total, pairs below, positives below, global index of the last
+ *       run start below (-1: none), positives before it}.  |sum over ranks| = AuROC, AuPRC of the whole list. */
+SS_API int32_t ss_auc_sort(ss_ctx* ctx, const void* labels_u8_dev, const void* scores_f64_dev, const void* keys_u64_dev,
+                           int64_t M, void** keys_sorted_out, void** labels_sorted_out);
+SS_API int32_t ss_auc_lower_bound(ss_ctx* ctx, const void* keys_sorted_dev, int64_t M, const uint64_t* query, int32_t nq,
+                                  int64_t* pos_out);
+SS_API int32_t ss_auc_segment_summary(ss_ctx* ctx, const void* keys_sorted_dev, const void* labels_sorted_dev, int64_t M,
+                                      int64_t* summary3);
+SS_API int32_t ss_auc_segment_integrate(ss_ctx* ctx, const void* keys_sorted_dev, const void* labels_sorted_dev, int64_t M,
+                                        const int64_t* global6, double* out2);
 /* Same for the entries of two device matrices (Ytrue != 0 is the label), column-major order. */
 SS_API int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, double* out2);
 

@@ -87,6 +87,10 @@ SIGNATURES = {
     "ss_topl_rows": (c_i32, [vp, vp, c_i32, vp, vp]),
     "ss_atl": (c_i32, [vp, vp, vp, c_i32, P(c_f64)]),
     "ss_auroc_auprc": (c_i32, [vp, vp, vp, c_i64, P(c_f64)]),
+    "ss_auc_sort": (c_i32, [vp, vp, vp, vp, c_i64, P(vp), P(vp)]),
+    "ss_auc_lower_bound": (c_i32, [vp, vp, c_i64, vp, c_i32, vp]),
+    "ss_auc_segment_summary": (c_i32, [vp, vp, vp, c_i64, vp]),
+    "ss_auc_segment_integrate": (c_i32, [vp, vp, vp, c_i64, vp, vp]),
     "ss_auroc_auprc_mat": (c_i32, [vp, vp, vp, P(c_f64)]),
     "ss_bedroc": (c_i32, [vp, vp, vp, c_i32, c_f64, P(c_f64)]),
     "ss_threshold_sweep": (c_i32, [vp, vp, vp, c_i32, P(c_f64)]),

@@ -900,6 +900,43 @@ int32_t ss_auroc_auprc(ss_ctx* ctx, const void* labels_u8_dev, const void* score
                        out2);
 }
 
+int32_t ss_auc_sort(ss_ctx* ctx, const void* labels_u8_dev, const void* scores_f64_dev, const void* keys_u64_dev, int64_t M,
+                    void** keys_sorted_out, void** labels_sorted_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(keys_sorted_out && labels_sorted_out && M >= 0, "ss_auc_sort: bad argument");
+    SS_REQUIRE(M == 0 || (labels_u8_dev && (scores_f64_dev || keys_u64_dev)), "ss_auc_sort: null input");
+    uint64_t* k = nullptr;
+    uint8_t* l = nullptr;
+    SS_TRY(auc_sort(ctx, static_cast<const uint8_t*>(labels_u8_dev), static_cast<const double*>(scores_f64_dev),
+                    static_cast<const uint64_t*>(keys_u64_dev), M, &k, &l));
+    *keys_sorted_out = k;
+    *labels_sorted_out = l;
+    return SS_OK;
+}
+
+int32_t ss_auc_lower_bound(ss_ctx* ctx, const void* keys_sorted_dev, int64_t M, const uint64_t* query, int32_t nq,
+                           int64_t* pos_out) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(M >= 0 && nq >= 0 && (nq == 0 || (query && pos_out)) && (M == 0 || keys_sorted_dev), "ss_auc_lower_bound: bad argument");
+    return auc_lower_bound(ctx, static_cast<const uint64_t*>(keys_sorted_dev), M, query, nq, pos_out);
+}
+
+int32_t ss_auc_segment_summary(ss_ctx* ctx, const void* keys_sorted_dev, const void* labels_sorted_dev, int64_t M,
+                               int64_t* summary3) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(summary3 && M >= 0 && (M == 0 || (keys_sorted_dev && labels_sorted_dev)), "ss_auc_segment_summary: bad argument");
+    return auc_segment_summary(ctx, static_cast<const uint64_t*>(keys_sorted_dev), static_cast<const uint8_t*>(labels_sorted_dev), M,
+                               summary3);
+}
+
+int32_t ss_auc_segment_integrate(ss_ctx* ctx, const void* keys_sorted_dev, const void* labels_sorted_dev, int64_t M,
+                                 const int64_t* global6, double* out2) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(global6 && out2 && M >= 0 && (M == 0 || (keys_sorted_dev && labels_sorted_dev)), "ss_auc_segment_integrate: bad argument");
+    return auc_segment_integrate(ctx, static_cast<const uint64_t*>(keys_sorted_dev), static_cast<const uint8_t*>(labels_sorted_dev), M,
+                                 global6, out2);
+}
+
 int32_t ss_auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Ytrue, const ss_mat* R, double* out2) {
     SS_ENTER(ctx);
     SS_REQUIRE(Ytrue && R && out2, "ss_auroc_auprc_mat: null argument");

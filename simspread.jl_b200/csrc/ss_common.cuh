@@ -131,6 +131,13 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
 int32_t jaccard_featurize(ss_ctx* ctx, const ss_mat* A, const ss_mat* B, double alpha, bool weighted, ss_mat* X);
 int32_t tanimoto_bits_featurize(ss_ctx* ctx, const uint64_t* FA, int64_t na, const uint64_t* FB, int64_t nb, int64_t words,
                                 double alpha, bool weighted, ss_mat* X);
+int32_t auc_sort(ss_ctx* ctx, const uint8_t* labels, const double* scores, const uint64_t* keys_in, int64_t M,
+                 uint64_t** keys_out, uint8_t** labels_out);
+int32_t auc_lower_bound(ss_ctx* ctx, const uint64_t* keys_sorted, int64_t M, const uint64_t* query_host, int nq,
+                        int64_t* pos_host);
+int32_t auc_segment_summary(ss_ctx* ctx, const uint64_t* keys, const uint8_t* lab, int64_t M, int64_t* summary3);
+int32_t auc_segment_integrate(ss_ctx* ctx, const uint64_t* keys, const uint8_t* lab, int64_t M, const int64_t* global6,
+                              double* out2);
 int32_t threshold_sweep(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int metric, double* out4);
 int32_t bedroc(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int rev, double alpha, double* out);
 

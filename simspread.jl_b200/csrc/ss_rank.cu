@@ -10,6 +10,8 @@
 //
 // Scores are mapped to uint64 keys that are monotone under Julia's isless
 // (-Inf < ... < -0.0 < 0.0 < ... < Inf < NaN, all NaNs equal).
+#include <algorithm>
+
 #include "ss_common.cuh"
 
 namespace {
@@ -491,12 +493,21 @@ __device__ CurveState cs_block_exclusive(CurveState agg, CurveState* block_total
     return cs_combine(wprefix, excl);
 }
 
+// What a sorted array is a SEGMENT of (multi-GPU AuROC: every rank holds one key range of the global order).
+// P / Mtot: positives / pairs of the whole list; idx0: pairs in the lower segments; init: scan state of everything
+// below (its `start` is a GLOBAL index).  A stand-alone array is the segment {P = its positives, Mtot = M, 0, identity}.
+struct CurveGlobal {
+    unsigned long long P, Mtot;
+    long long idx0;
+    CurveState init;
+};
+
 // EMIT == false: write the block aggregate.  EMIT == true: use the scanned block prefixes and add
 // one trapezoid per run boundary into partial[block] (roc) / partial[nblocks + block] (pr).
 template <bool EMIT>
 __global__ void __launch_bounds__(CV_TPB)
     curve_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ lab, int64_t M,
-                 CurveState* __restrict__ block_state, const unsigned long long* __restrict__ totals,
+                 CurveState* __restrict__ block_state, const CurveGlobal* __restrict__ glob,
                  double* __restrict__ partial, int64_t nblocks) {
     const int64_t base = int64_t(blockIdx.x) * CV_TILE + int64_t(threadIdx.x) * CV_ITEMS;
     uint64_t k[CV_ITEMS + 1];
@@ -524,24 +535,29 @@ __global__ void __launch_bounds__(CV_TPB)
         if (threadIdx.x == 0) block_state[blockIdx.x] = total;
         return;
     }
-    CurveState run = cs_combine(block_state[blockIdx.x], excl);  // exclusive prefix over the whole array
-    const double P = double(totals[0]);
-    const double N = double((unsigned long long)M - totals[0]);
+    const CurveGlobal g = *glob;
+    // exclusive prefix over the whole (global) list; local run starts are shifted to global indices
+    CurveState loc = cs_combine(block_state[blockIdx.x], excl);
+    if (loc.start >= 0) loc.start += g.idx0;
+    CurveState run = cs_combine(g.init, loc);
+    const double P = double(g.P);
+    const double N = double(g.Mtot - g.P);
     double roc = 0.0, pr = 0.0;
 #pragma unroll
     for (int i = 0; i < CV_ITEMS; ++i) {
         const int64_t idx = base + i;
         if (idx < M) {
-            const bool is_start = (idx == 0) || (k[i + 1] != k[i]);
-            if (is_start && idx > 0) {
-                // lower threshold = previous run (start p), higher threshold = this run (start idx)
+            const bool is_start = (idx == 0) || (k[i + 1] != k[i]);  // keys never straddle two segments
+            const long long gidx = (long long)idx + g.idx0;
+            if (is_start && run.start >= 0) {
+                // lower threshold = previous run (start p), higher threshold = this run (start gidx)
                 const double p = double(run.start);
                 const double tp1 = P - double(run.startpos), fp1 = N - (p - double(run.startpos));
-                const double tp2 = P - double(run.pos), fp2 = N - (double(idx) - double(run.pos));
+                const double tp2 = P - double(run.pos), fp2 = N - (double(gidx) - double(run.pos));
                 roc += (fp2 / N - fp1 / N) * (tp1 / P + tp2 / P) * 0.5;
                 pr += (tp2 / P - tp1 / P) * (tp1 / (tp1 + fp1) + tp2 / (tp2 + fp2)) * 0.5;
             }
-            CurveState e = {(unsigned long long)l[i], is_start ? (long long)idx : -1ll, 0ull};
+            CurveState e = {(unsigned long long)l[i], is_start ? gidx : -1ll, 0ull};
             run = cs_combine(run, e);
         }
     }
@@ -565,7 +581,8 @@ __global__ void __launch_bounds__(CV_TPB)
 
 // single-block exclusive scan of the block aggregates (in place) + grand total of positives
 __global__ void __launch_bounds__(1024)
-    curve_scan_kernel(CurveState* __restrict__ st, int64_t n, unsigned long long* __restrict__ totals) {
+    curve_scan_kernel(CurveState* __restrict__ st, int64_t n, int64_t M, CurveGlobal* __restrict__ glob,
+                      CurveState* __restrict__ summary) {
     __shared__ CurveState part[1024];
     const int t = threadIdx.x;
     const int64_t chunk = (n + 1023) / 1024;
@@ -581,7 +598,11 @@ __global__ void __launch_bounds__(1024)
             part[i] = run;
             run = cs_combine(run, v);
         }
-        totals[0] = run.pos;
+        glob->P = run.pos;  // stand-alone list; a segment caller overwrites *glob with the global picture
+        glob->Mtot = (unsigned long long)M;
+        glob->idx0 = 0;
+        glob->init = cs_identity();
+        *summary = run;     // (positives, last run start, positives before it) of this array
     }
     __syncthreads();
     CurveState run = part[t];
@@ -594,7 +615,7 @@ __global__ void __launch_bounds__(1024)
 
 // out[0] = |sum roc partials|, out[1] = |sum pr partials|
 __global__ void __launch_bounds__(1024)
-    curve_final_kernel(const double* __restrict__ partial, int64_t nblocks, double* __restrict__ out) {
+    curve_final_kernel(const double* __restrict__ partial, int64_t nblocks, double* __restrict__ out, int keep_sign) {
     __shared__ double sa[1024], sb[1024];
     const int t = threadIdx.x;
     double a = 0.0, b = 0.0;
@@ -613,8 +634,8 @@ __global__ void __launch_bounds__(1024)
         __syncthreads();
     }
     if (t == 0) {
-        out[0] = fabs(sa[0]);
-        out[1] = fabs(sb[0]);
+        out[0] = keep_sign ? sa[0] : fabs(sa[0]);
+        out[1] = keep_sign ? sb[0] : fabs(sb[0]);
     }
 }
 
@@ -804,6 +825,21 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// pos[q] = number of keys < query[q] in the ascending array (one thread per query)
+__global__ void __launch_bounds__(64)
+    lower_bound_kernel(const uint64_t* __restrict__ keys, int64_t M, const uint64_t* __restrict__ query, int nq,
+                       long long* __restrict__ pos) {
+    const int q = blockIdx.x * 64 + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t v = query[q];
+    int64_t lo = 0, hi = M;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    pos[q] = lo;
+}
+
 // stable ascending LSD radix sort of the (key, label) pairs; *kout / *lout point at the sorted arrays
 int32_t sort_pairs(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB, uint8_t* labB, int64_t M,
                    uint64_t** kout_p, uint8_t** lout_p) {
@@ -853,27 +889,45 @@ int32_t sort_pairs(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB,
     return SS_OK;
 }
 
+// scratch of the curve integration over M sorted pairs
+struct CurveBufs {
+    CurveState* bstate;
+    double* partial;
+    CurveGlobal* glob;
+    CurveState* summary;
+    double* dout;
+    int64_t cblocks;
+};
+
+int32_t curve_bufs(ss_ctx* ctx, int64_t M, CurveBufs* b) {
+    using namespace ss;
+    void* p;
+    b->cblocks = ceil_div(std::max<int64_t>(M, 1), CV_TILE);
+    SS_TRY(scratch_get(ctx, 12, size_t(b->cblocks) * sizeof(CurveState) + size_t(2 * b->cblocks) * 8 + 256, &p));
+    b->bstate = static_cast<CurveState*>(p);
+    b->partial = reinterpret_cast<double*>(b->bstate + b->cblocks);
+    b->glob = reinterpret_cast<CurveGlobal*>(b->partial + 2 * b->cblocks);
+    b->summary = reinterpret_cast<CurveState*>(b->glob + 1);
+    b->dout = reinterpret_cast<double*>(b->summary + 1);
+    return SS_OK;
+}
+
 int32_t sort_and_integrate(ss_ctx* ctx, uint64_t* keysA, uint8_t* labA, uint64_t* keysB, uint8_t* labB, int64_t M,
                            double* out2) {
     using namespace ss;
-    void* p;
     uint64_t* kin;
     uint8_t* lin;
     SS_TRY(sort_pairs(ctx, keysA, labA, keysB, labB, M, &kin, &lin));
     // curve integration over (kin, lin)
-    const int64_t cblocks = ceil_div(M, CV_TILE);
-    SS_TRY(scratch_get(ctx, 12, size_t(cblocks) * sizeof(CurveState) + size_t(2 * cblocks) * 8 + 64, &p));
-    CurveState* bstate = static_cast<CurveState*>(p);
-    double* partial = reinterpret_cast<double*>(bstate + cblocks);
-    unsigned long long* totals = reinterpret_cast<unsigned long long*>(partial + 2 * cblocks);
-    double* dout = reinterpret_cast<double*>(totals + 2);
-    curve_kernel<false><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, nullptr, nullptr, cblocks);
-    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(bstate, cblocks, totals);
-    curve_kernel<true><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, totals, partial, cblocks);
-    curve_final_kernel<<<1, 1024, 0, ctx->stream>>>(partial, cblocks, dout);
+    CurveBufs b;
+    SS_TRY(curve_bufs(ctx, M, &b));
+    curve_kernel<false><<<unsigned(b.cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, b.bstate, nullptr, nullptr, b.cblocks);
+    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(b.bstate, b.cblocks, M, b.glob, b.summary);
+    curve_kernel<true><<<unsigned(b.cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, b.bstate, b.glob, b.partial, b.cblocks);
+    curve_final_kernel<<<1, 1024, 0, ctx->stream>>>(b.partial, b.cblocks, b.dout, 0);
     ctx->launches += 4;
     SS_CHECK_CUDA(cudaGetLastError());
-    SS_CHECK_CUDA(cudaMemcpyAsync(out2, dout, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaMemcpyAsync(out2, b.dout, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }
@@ -979,13 +1033,15 @@ int32_t threshold_sweep(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int metri
     SS_TRY(sort_pairs(ctx, kA, lA, kB, lB, M, &kin, &lin));
     const int64_t cblocks = ceil_div(M, CV_TILE);
     void* p;
-    SS_TRY(scratch_get(ctx, 12, size_t(cblocks) * sizeof(CurveState) + size_t(4 * cblocks) * 8 + 128, &p));
+    SS_TRY(scratch_get(ctx, 12, size_t(cblocks) * sizeof(CurveState) + size_t(4 * cblocks) * 8 + 256, &p));
     CurveState* bstate = static_cast<CurveState*>(p);
     double* partial = reinterpret_cast<double*>(bstate + cblocks);
-    unsigned long long* totals = reinterpret_cast<unsigned long long*>(partial + 4 * cblocks);
-    double* dout = reinterpret_cast<double*>(totals + 2);
+    CurveGlobal* glob = reinterpret_cast<CurveGlobal*>(partial + 4 * cblocks);
+    CurveState* summary = reinterpret_cast<CurveState*>(glob + 1);
+    const unsigned long long* totals = &glob->P;  // positives of the whole list
+    double* dout = reinterpret_cast<double*>(summary + 1);
     curve_kernel<false><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, nullptr, nullptr, cblocks);
-    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(bstate, cblocks, totals);
+    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(bstate, cblocks, M, glob, summary);
     sweep_kernel<0><<<unsigned(cblocks), CV_TPB, 0, ctx->stream>>>(kin, lin, M, bstate, totals, metric, 0.0, partial, cblocks);
     sweep_final_kernel<<<1, 1024, 0, ctx->stream>>>(partial, cblocks, dout);
     ctx->launches += 4;
@@ -1055,6 +1111,99 @@ int32_t bedroc(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, int rev, double al
     const double fac = Ra * sinh(alpha / 2.0) / (cosh(alpha / 2.0) - cosh(alpha / 2.0 - alpha * Ra));
     const double cte = 1.0 / (1.0 - exp(alpha * (1.0 - Ra)));
     *out = ssum * fac / rand_sum + cte;
+    return SS_OK;
+}
+
+// ---- AuROC / AuPRC of a list that is spread over several GPUs -----------------------------------
+// Every rank sorts what it holds, the ranks agree on key splitters and exchange the pairs so that rank r owns one
+// contiguous key range of the global order (host side: simspread.jl_b200/sharded.py), then each rank integrates
+// the trapezoids of ITS range given what lies below it; the signed partial areas add up to the global ones.
+
+// (scores, labels) -> ascending (key, label) arrays in the context's sort buffers (valid until the next metric call)
+int32_t auc_sort(ss_ctx* ctx, const uint8_t* labels, const double* scores, const uint64_t* keys_in, int64_t M,
+                 uint64_t** keys_out, uint8_t** labels_out) {
+    uint64_t *kA, *kB;
+    uint8_t *lA, *lB;
+    SS_TRY(alloc_sort_buffers(ctx, std::max<int64_t>(M, 1), &kA, &kB, &lA, &lB));
+    *keys_out = kA;
+    *labels_out = lA;
+    if (M == 0) return SS_OK;
+    if (keys_in) {  // pairs that already carry keys (received from the peers)
+        SS_CHECK_CUDA(cudaMemcpyAsync(kA, keys_in, size_t(M) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        SS_CHECK_CUDA(cudaMemcpyAsync(lA, labels, size_t(M), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        int grid = int(ceil_div(M, 256 * 8));
+        if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+        make_keys_kernel<<<grid, 256, 0, ctx->stream>>>(scores, labels, M, kA, lA);
+        ctx->launches++;
+    }
+    SS_TRY(sort_pairs(ctx, kA, lA, kB, lB, M, keys_out, labels_out));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int32_t auc_lower_bound(ss_ctx* ctx, const uint64_t* keys_sorted, int64_t M, const uint64_t* query_host, int nq,
+                        int64_t* pos_host) {
+    if (nq == 0) return SS_OK;
+    void* p;
+    SS_TRY(scratch_get(ctx, 12, size_t(nq) * 16 + 64, &p));
+    uint64_t* dq = static_cast<uint64_t*>(p);
+    long long* dp = reinterpret_cast<long long*>(dq + nq);
+    SS_CHECK_CUDA(cudaMemcpyAsync(dq, query_host, size_t(nq) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    lower_bound_kernel<<<unsigned(ceil_div(nq, 64)), 64, 0, ctx->stream>>>(keys_sorted, M, dq, nq, dp);
+    ctx->launches++;
+    SS_CHECK_CUDA(cudaGetLastError());
+    SS_CHECK_CUDA(cudaMemcpyAsync(pos_host, dp, size_t(nq) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// summary3 = {positives, index of the last run start (-1: empty), positives before that run start} of a sorted array
+int32_t auc_segment_summary(ss_ctx* ctx, const uint64_t* keys, const uint8_t* lab, int64_t M, int64_t* summary3) {
+    if (M == 0) {
+        summary3[0] = 0;
+        summary3[1] = -1;
+        summary3[2] = 0;
+        return SS_OK;
+    }
+    CurveBufs b;
+    SS_TRY(curve_bufs(ctx, M, &b));
+    curve_kernel<false><<<unsigned(b.cblocks), CV_TPB, 0, ctx->stream>>>(keys, lab, M, b.bstate, nullptr, nullptr, b.cblocks);
+    curve_scan_kernel<<<1, 1024, 0, ctx->stream>>>(b.bstate, b.cblocks, M, b.glob, b.summary);
+    ctx->launches += 2;
+    SS_CHECK_CUDA(cudaGetLastError());
+    CurveState h;
+    SS_CHECK_CUDA(cudaMemcpyAsync(&h, b.summary, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    summary3[0] = int64_t(h.pos);
+    summary3[1] = h.start;
+    summary3[2] = int64_t(h.startpos);
+    return SS_OK;
+}
+
+// signed trapezoid sums of the run boundaries inside this segment, including the joint to the segment below.
+// global6 = {P, Mtot, idx0, init.pos, init.start (global index, -1: nothing below), init.startpos}; must follow
+// auc_segment_summary on the same arrays (re-uses its block scan).
+int32_t auc_segment_integrate(ss_ctx* ctx, const uint64_t* keys, const uint8_t* lab, int64_t M, const int64_t* global6,
+                              double* out2) {
+    out2[0] = out2[1] = 0.0;
+    if (M == 0) return SS_OK;
+    CurveBufs b;
+    SS_TRY(curve_bufs(ctx, M, &b));
+    CurveGlobal g;
+    g.P = (unsigned long long)global6[0];
+    g.Mtot = (unsigned long long)global6[1];
+    g.idx0 = global6[2];
+    g.init.pos = (unsigned long long)global6[3];
+    g.init.start = global6[4];
+    g.init.startpos = (unsigned long long)global6[5];
+    SS_CHECK_CUDA(cudaMemcpyAsync(b.glob, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
+    curve_kernel<true><<<unsigned(b.cblocks), CV_TPB, 0, ctx->stream>>>(keys, lab, M, b.bstate, b.glob, b.partial, b.cblocks);
+    curve_final_kernel<<<1, 1024, 0, ctx->stream>>>(b.partial, b.cblocks, b.dout, 1);
+    ctx->launches += 2;
+    SS_CHECK_CUDA(cudaGetLastError());
+    SS_CHECK_CUDA(cudaMemcpyAsync(out2, b.dout, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }
 

@@ -86,8 +86,8 @@ class ShardedPredict:
 class _CudaView:
     """Minimal __cuda_array_interface__ carrier: a torch view of library-owned device memory."""
 
-    def __init__(self, ptr: int, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr: int, shape, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2}
 
 
@@ -217,20 +217,143 @@ class LibBackend:
                                       self.vkt.h if clean else None))
 
 
-def global_auroc_auprc(ss, ctx, torch, dist, y_local, r_local, world: int, rank: int):
+def combine_segment_summaries(sizes, summaries, rank: int):
+    """global6 of `ss_auc_segment_integrate` for segment `rank`, from the (pairs, (positives, last run start,
+    positives before it)) of every segment in ascending key order.  Pure host arithmetic (CPU-testable)."""
+    P = sum(int(su[0]) for su in summaries)
+    Mtot = sum(int(m) for m in sizes)
+    idx0 = pos_below = 0
+    init_start, init_startpos = -1, 0
+    for r in range(rank):
+        m, (pos, start, startpos) = int(sizes[r]), (int(x) for x in summaries[r])
+        if start >= 0:
+            init_start, init_startpos = idx0 + start, pos_below + startpos
+        idx0 += m
+        pos_below += pos
+    return [P, Mtot, idx0, pos_below, init_start, init_startpos]
+
+
+def pick_splitters(samples_u64, world: int):
+    """world - 1 key splitters from the gathered, regularly spaced samples of every rank's sorted keys."""
+    import numpy as np
+    sm = np.sort(np.asarray(samples_u64, dtype=np.uint64).ravel())
+    if sm.size == 0:
+        return np.zeros(world - 1, dtype=np.uint64)
+    return sm[[min(sm.size - 1, (i * sm.size) // world) for i in range(1, world)]].astype(np.uint64)
+
+
+class LibAucBackend:
+    """Device side of the sample-sort AuROC: libsimspread_b200 on this rank's GPU.  The sorted (key, label) arrays
+    live in the context's sort buffers; `keys` / `labs` are torch views of them (uint64 keys moved as int64 bits)."""
+
+    def __init__(self, ss, ctx, torch, dev):
+        from ._lib import check
+        self.L, self.ctx, self.torch, self.dev, self.check = ss.lib(), ctx, torch, dev, check
+        self.pk, self.pl, self.m = C.c_void_p(), C.c_void_p(), 0
+
+    def sort(self, labels, scores=None, keys=None):
+        t = self.torch
+        self.m = int(labels.numel())
+        t.cuda.synchronize(self.dev)
+        self.check(self.L.ss_auc_sort(self.ctx.h, C.c_void_p(labels.data_ptr()),
+                                      C.c_void_p(scores.data_ptr()) if scores is not None else None,
+                                      C.c_void_p(keys.data_ptr()) if keys is not None else None, self.m,
+                                      C.byref(self.pk), C.byref(self.pl)))
+        n = max(self.m, 1)
+        return (t.as_tensor(_CudaView(self.pk.value, (n,), "<i8"), device=self.dev)[:self.m],
+                t.as_tensor(_CudaView(self.pl.value, (n,), "|u1"), device=self.dev)[:self.m])
+
+    def lower_bound(self, split_u64):
+        import numpy as np
+        cut = np.zeros(len(split_u64), dtype=np.int64)
+        self.check(self.L.ss_auc_lower_bound(self.ctx.h, self.pk, self.m, split_u64.ctypes.data, len(split_u64), cut.ctypes.data))
+        return cut
+
+    def summary(self):
+        import numpy as np
+        out = np.zeros(3, dtype=np.int64)
+        self.check(self.L.ss_auc_segment_summary(self.ctx.h, self.pk, self.pl, self.m, out.ctypes.data))
+        return out
+
+    def integrate(self, g6):
+        import numpy as np
+        g = np.asarray(g6, dtype=np.int64)
+        part = (C.c_double * 2)()
+        self.check(self.L.ss_auc_segment_integrate(self.ctx.h, self.pk, self.pl, self.m, g.ctypes.data, part))
+        return float(part[0]), float(part[1])
+
+
+def samplesort_auroc_auprc(backend, torch, dist, labels, scores, world: int, rank: int, samples_per_rank: int = 64):
+    """Choreography of the distributed AuROC / AuPRC (see `global_auroc_auprc`).  `backend` does the per-rank work
+    (LibAucBackend on a GPU; tests/test_sharded_gloo.py drives it with a NumPy double over gloo)."""
+    import numpy as np
+    dev = labels.device
+    m = int(labels.numel())
+    keys, labs = backend.sort(labels, scores=scores)
+    # 1. splitters from regularly spaced samples of every rank's sorted keys
+    ns = samples_per_rank
+    samp = torch.zeros(ns, dtype=torch.int64, device=dev)
+    have = torch.tensor([min(ns, m)], dtype=torch.int64, device=dev)
+    if m:
+        pos = torch.linspace(0, m - 1, steps=min(ns, m), device=dev).to(torch.int64)
+        samp[:pos.numel()] = keys[pos]
+    all_s = [torch.zeros_like(samp) for _ in range(world)]
+    all_n = [torch.zeros_like(have) for _ in range(world)]
+    dist.all_gather(all_s, samp)
+    dist.all_gather(all_n, have)
+    gathered = np.concatenate([t.cpu().numpy().view(np.uint64)[:int(n.item())] for t, n in zip(all_s, all_n)])
+    split = pick_splitters(gathered, world)
+    # 2. every pair goes to the rank that owns its key range (keys < splitter[r] -> ranks <= r): one all-to-all
+    cut = np.maximum.accumulate(backend.lower_bound(split)) if world > 1 else np.zeros(0, dtype=np.int64)
+    send = np.diff(np.concatenate([[0], cut, [m]])).astype(np.int64)
+    send_t = torch.from_numpy(send).to(dev)
+    recv_t = torch.zeros_like(send_t)
+    dist.all_to_all_single(recv_t, send_t)
+    recv = recv_t.cpu().numpy()
+    mr = int(recv.sum())
+    rk = torch.empty(max(mr, 1), dtype=torch.int64, device=dev)[:mr]
+    rl = torch.empty(max(mr, 1), dtype=torch.uint8, device=dev)[:mr]
+    dist.all_to_all_single(rk, keys.contiguous(), output_split_sizes=recv.tolist(), input_split_sizes=send.tolist())
+    dist.all_to_all_single(rl, labs.contiguous(), output_split_sizes=recv.tolist(), input_split_sizes=send.tolist())
+    # 3. sort the received runs, exchange the 3-integer summaries, integrate this key range
+    backend.sort(rl, keys=rk)
+    summ = backend.summary()
+    mine = torch.tensor([mr, int(summ[0]), int(summ[1]), int(summ[2])], dtype=torch.int64, device=dev)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    every = [t.cpu().numpy() for t in every]
+    g6 = combine_segment_summaries([e[0] for e in every], [e[1:] for e in every], rank)
+    part = backend.integrate(g6)
+    out = torch.tensor([part[0], part[1]], dtype=torch.float64, device=dev)
+    dist.all_reduce(out)
+    return abs(float(out[0].item())), abs(float(out[1].item()))
+
+
+def global_auroc_auprc(ss, ctx, torch, dist, y_local, r_local, world: int, rank: int, method: str = "samplesort"):
     """AuROC / AuPRC over the scores of ALL ranks (reference src/performance.jl:49-63, 74-89 on the
     concatenation of the per-rank (label, score) lists -- both areas are order-independent).
 
-    Exchange step: the per-rank score slabs (float64) and labels (uint8) are gathered on rank 0 with one NCCL
-    gather each (padded to the largest slab), and rank 0 runs the device sort + scan (`ss_auroc_auprc`) on the
-    concatenation; the result is broadcast.  Needs 9 B per score plus the 18 B per score of sort buffers on rank
-    0 (C4 on 8 GPUs: 45 GB + 90 GB of 180 GB).  A sample-sort over the ranks would remove that limit; per-query
-    metrics (recall@L / precision@L) need no exchange at all."""
-    from ._lib import check
+    method="samplesort" (default): every rank radix-sorts its pairs on the device (`ss_auc_sort`), the ranks agree
+    on world-1 key splitters from regularly spaced samples, ONE NCCL all-to-all moves every pair to the rank that
+    owns its key range (equal keys never straddle two ranks), each rank re-sorts what it received and integrates
+    the trapezoids of its range given the counts below it (`ss_auc_segment_summary` / `_integrate`; the summaries
+    are all-gathered, 3 integers per rank), and the signed partial areas are all-reduced.  Memory and work per
+    rank stay ~1/world of the list.
+    method="gather": NCCL gather of the slabs to rank 0 and the single-GPU kernel there (needs 27 B per score of
+    the WHOLE list on rank 0)."""
     dev = r_local.device
-    scores = r_local.reshape(-1).to(torch.float64)
-    labels = (y_local.reshape(-1) != 0).to(torch.uint8)
+    scores = r_local.reshape(-1).to(torch.float64).contiguous()
+    labels = (y_local.reshape(-1) != 0).to(torch.uint8).contiguous()
     assert scores.numel() == labels.numel(), "The number of scores must be equal to the number of labels"
+    if method == "gather" or world == 1:
+        return _gather_auroc_auprc(ss, ctx, torch, dist, labels, scores, world, rank)
+    assert method == "samplesort"
+    return samplesort_auroc_auprc(LibAucBackend(ss, ctx, torch, dev), torch, dist, labels, scores, world, rank)
+
+
+def _gather_auroc_auprc(ss, ctx, torch, dist, labels, scores, world: int, rank: int):
+    from ._lib import check
+    dev = scores.device
     n = torch.tensor([scores.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     if world > 1:

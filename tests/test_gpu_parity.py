@@ -780,7 +780,10 @@ def test_two_layer_nbi_recommender_shape(ss, o):
     assert np.array_equal(idx.to_host().reshape(users, L), order)
 
 
-@pytest.mark.parametrize("users,items,dens,L", [(300, 200, 0.05, 16), (1000, 2600, 0.01, 16), (64, 40000, 0.002, 32)])
+# (40, 3000, 0.5): ~1500 targets per source -> several staging passes of the fused kernel (1024 items each) and the
+# > 64-target tail loop of every co-rater; (3, 70000, 0.01): fewer sources than clusters, column tail of the row
+@pytest.mark.parametrize("users,items,dens,L", [(300, 200, 0.05, 16), (1000, 2600, 0.01, 16), (64, 40000, 0.002, 32),
+                                                (40, 3000, 0.5, 20), (3, 70001, 0.01, 8)])
 def test_sparse_recommender_topl_against_dense_path(ss, o, users, items, dens, L):
     """Config-5 form at test scale: two-hop CSR expansion with L2-resident accumulators and fused
     top-L, against the dense chain (ss_predict_source) + ss_topl_rows and the oracle."""
@@ -867,3 +870,62 @@ def test_tanimoto_bits_featurize_bit_exact(ss, o, na, nb, words):
     for alpha, weighted in ((0.0, True), (0.2, True), (0.2, False)):
         got = ss.tanimoto_featurize_bits(FA, FB, alpha, weighted)
         assert np.array_equal(got, o.cutoff(T, alpha, weighted))
+
+
+# ---------------------------------------------------------------------------------------------
+# AuROC / AuPRC of a list split into key ranges (the per-rank work of the multi-GPU form)
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("m,nseg", [(5000, 3), (100001, 8), (64, 5)])
+def test_auc_key_range_segments_add_up(ss, o, m, nseg):
+    """ss_auc_sort / _lower_bound / _segment_summary / _segment_integrate: the sorted list is cut at key splitters
+    (equal keys never straddle a cut), every range is integrated on its own with what lies below it, and the signed
+    partial areas add up to ss_auroc_auprc of the whole list and to the oracle."""
+    import torch
+    from simspread_b200._lib import check
+    from simspread_b200.sharded import combine_segment_summaries, pick_splitters
+    rng = np.random.default_rng(m + nseg)
+    sc = np.round(rng.random(m), 3)  # many ties
+    sc[:m // 20] = 0.0
+    sc[m // 20:m // 16] = -0.0
+    lb = (rng.random(m) < 0.1 + 0.6 * sc).astype(np.uint8)
+    ctx = ss.Context.default()
+    L = ss.lib()
+    dev = torch.device("cuda", ctx.device)
+    ts, tl = torch.from_numpy(sc).to(dev), torch.from_numpy(lb).to(dev)
+    whole = (C.c_double * 2)()
+    check(L.ss_auroc_auprc(ctx.h, C.c_void_p(tl.data_ptr()), C.c_void_p(ts.data_ptr()), m, whole))
+    assert whole[0] == pytest.approx(o.AuROC(lb > 0, sc), rel=1e-12) and whole[1] == pytest.approx(o.AuPRC(lb > 0, sc), rel=1e-12)
+    pk, pl = C.c_void_p(), C.c_void_p()
+    check(L.ss_auc_sort(ctx.h, C.c_void_p(tl.data_ptr()), C.c_void_p(ts.data_ptr()), None, m, C.byref(pk), C.byref(pl)))
+    keys = np.sort(o._isless_key(sc).astype(np.uint64))
+    split = pick_splitters(keys[:: max(1, m // 40)], nseg)
+    split[0] = keys[0]  # an empty first range
+    cut = np.zeros(nseg - 1, dtype=np.int64)
+    check(L.ss_auc_lower_bound(ctx.h, pk, m, split.ctypes.data, nseg - 1, cut.ctypes.data))
+    assert np.array_equal(cut, np.searchsorted(keys, split, side="left"))
+    bounds = np.concatenate([[0], np.maximum.accumulate(cut), [m]])
+    # the segments are slices of the sorted arrays; copy them out (the sort buffers are reused below)
+    from simspread_b200.sharded import _CudaView
+    K = torch.as_tensor(_CudaView(pk.value, (m,), "<i8"), device=dev).clone()
+    Lb = torch.as_tensor(_CudaView(pl.value, (m,), "|u1"), device=dev).clone()
+    assert np.array_equal(K.cpu().numpy().view(np.uint64), keys)
+    segs = [(K[bounds[i]:bounds[i + 1]].contiguous(), Lb[bounds[i]:bounds[i + 1]].contiguous()) for i in range(nseg)]
+    sizes, summ = [], []
+    for k_, l_ in segs:
+        out = np.zeros(3, dtype=np.int64)
+        check(L.ss_auc_segment_summary(ctx.h, C.c_void_p(k_.data_ptr()), C.c_void_p(l_.data_ptr()), k_.numel(), out.ctypes.data))
+        sizes.append(k_.numel())
+        summ.append(out.copy())
+    assert sum(int(s_[0]) for s_ in summ) == int(lb.sum()) and sizes[0] == 0 and tuple(summ[0]) == (0, -1, 0)
+    roc = pr = 0.0
+    for r_, (k_, l_) in enumerate(segs):
+        out = np.zeros(3, dtype=np.int64)
+        check(L.ss_auc_segment_summary(ctx.h, C.c_void_p(k_.data_ptr()), C.c_void_p(l_.data_ptr()), k_.numel(), out.ctypes.data))
+        g6 = np.array(combine_segment_summaries(sizes, summ, r_), dtype=np.int64)
+        part = (C.c_double * 2)()
+        check(L.ss_auc_segment_integrate(ctx.h, C.c_void_p(k_.data_ptr()), C.c_void_p(l_.data_ptr()), k_.numel(), g6.ctypes.data, part))
+        roc += part[0]
+        pr += part[1]
+    assert abs(roc) == pytest.approx(whole[0], rel=1e-12) and abs(pr) == pytest.approx(whole[1], rel=1e-12)

@@ -124,3 +124,113 @@ def test_plan_partitions():
             cover += list(range(p.q0, p.q0 + p.nq_local))
         assert cover == list(range(n))
         assert all(p.nt_padded >= n and p.nt_padded - n < w for p in plans)
+
+
+# ---------------------------------------------------------------------------------------------
+# AuROC / AuPRC of a list spread over the ranks (sample sort + per-range integration), SURVEY 8f-1
+# ---------------------------------------------------------------------------------------------
+
+
+class NumpyAucBackend:
+    """Test double with the LibAucBackend interface: the per-rank device work restated in NumPy
+    (keys = the oracle's isless image of the scores, moved around as int64 bit patterns)."""
+
+    def __init__(self, o):
+        self.o = o
+        self.k = np.zeros(0, np.uint64)
+        self.l = np.zeros(0, np.uint8)
+
+    def sort(self, labels, scores=None, keys=None):
+        lab = labels.numpy().astype(np.uint8)
+        k = self.o._isless_key(scores.numpy()).astype(np.uint64) if scores is not None else keys.numpy().view(np.uint64)
+        order = np.argsort(k, kind="stable")
+        self.k, self.l = k[order], lab[order]
+        return torch.from_numpy(self.k.view(np.int64).copy()), torch.from_numpy(self.l.copy())
+
+    def lower_bound(self, split):
+        return np.searchsorted(self.k, split, side="left").astype(np.int64)
+
+    def _starts(self):
+        if self.k.size == 0:
+            return np.zeros(0, np.int64)
+        return np.flatnonzero(np.concatenate([[True], self.k[1:] != self.k[:-1]])).astype(np.int64)
+
+    def summary(self):
+        st = self._starts()
+        if st.size == 0:
+            return np.array([0, -1, 0], dtype=np.int64)
+        return np.array([int(self.l.sum()), int(st[-1]), int(self.l[:st[-1]].sum())], dtype=np.int64)
+
+    def integrate(self, g6):
+        P, Mtot, idx0, pos_below, init_start, init_startpos = (int(x) for x in g6)
+        N = Mtot - P
+        st = self._starts()
+        cum = np.concatenate([[0], np.cumsum(self.l.astype(np.int64))])
+        pts = [(idx0 + int(s), pos_below + int(cum[s])) for s in st]  # (global index of a run start, positives before it)
+        if init_start >= 0:
+            pts = [(init_start, init_startpos)] + pts
+        roc = pr = 0.0
+        for (p1, b1), (p2, b2) in zip(pts[:-1], pts[1:]):  # lower threshold, higher threshold
+            tp1, fp1, tp2, fp2 = P - b1, N - (p1 - b1), P - b2, N - (p2 - b2)
+            roc += (fp2 / N - fp1 / N) * (tp1 / P + tp2 / P) * 0.5
+            pr += (tp2 / P - tp1 / P) * (tp1 / (tp1 + fp1) + tp2 / (tp2 + fp2)) * 0.5
+        return roc, pr
+
+
+def _auc_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import simspread_b200  # noqa: F401
+    from simspread_b200.sharded import samplesort_auroc_auprc
+    from oracle import simspread_oracle as o
+    ok = True
+    for case, sizes in enumerate([(700, 1300), (0, 900), (5, 3)]):
+        rng = np.random.default_rng(100 + case)
+        parts = []
+        for m in sizes:  # every rank builds all slabs, keeps its own: ties inside and across slabs, -0.0 / 0.0
+            sc = np.round(rng.random(m), 2)
+            sc[: m // 10] = 0.0
+            sc[m // 10: m // 8] = -0.0
+            lb = (rng.random(m) < 0.2 + 0.5 * sc).astype(np.uint8)
+            parts.append((sc, lb))
+        if sum(int(p[1].sum()) for p in parts) == 0:
+            parts[-1][1][0] = 1
+        sc, lb = parts[rank]
+        got = samplesort_auroc_auprc(NumpyAucBackend(o), torch, dist, torch.from_numpy(lb.copy()), torch.from_numpy(sc.copy()),
+                                     world, rank, samples_per_rank=8)
+        S = np.concatenate([p[0] for p in parts])
+        Lb = np.concatenate([p[1] for p in parts])
+        want = (o.AuROC(Lb > 0, S), o.AuPRC(Lb > 0, S))
+        ok = ok and abs(got[0] - want[0]) <= 1e-12 * abs(want[0]) and abs(got[1] - want[1]) <= 1e-12 * abs(want[1])
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_samplesort_auroc_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_auc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
+def test_segment_summaries_combine():
+    sys.path.insert(0, ROOT)
+    import simspread_b200  # noqa: F401
+    from simspread_b200.sharded import combine_segment_summaries, pick_splitters
+    sizes = [4, 0, 3, 5]
+    summ = [(2, 3, 1), (0, -1, 0), (1, 0, 0), (3, 2, 1)]
+    assert combine_segment_summaries(sizes, summ, 0) == [6, 12, 0, 0, -1, 0]
+    assert combine_segment_summaries(sizes, summ, 1) == [6, 12, 4, 2, 3, 1]
+    assert combine_segment_summaries(sizes, summ, 2) == [6, 12, 4, 2, 3, 1]       # the empty segment changes nothing
+    assert combine_segment_summaries(sizes, summ, 3) == [6, 12, 7, 3, 4, 2]       # last run start below: 4 + 0
+    sp = pick_splitters(np.array([5, 1, 9, 3, 7, 2, 8, 4], dtype=np.uint64), 4)
+    assert sp.dtype == np.uint64 and list(sp) == [3, 5, 8] and len(pick_splitters(np.zeros(0, np.uint64), 3)) == 2
