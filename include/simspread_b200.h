@@ -216,7 +216,7 @@ SS_API int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y,
  * on the graph [0 Y; Y' 0], reduced to `sortperm(rev=true)[1:L]` per source, src/performance.jl:315):
  * Y = CSR of the source x target graph, YT = CSR of its transpose.  F is never materialised.  Sources
  * [s_begin, s_end) are processed (shard the range across GPUs); idx_out is L x sources (0-based target
- * indices, -1 padding), val_out (optional) the matching scores, dense L x sources with ld == L.  L <= 32. */
+ * indices, -1 padding), val_out (optional) the matching scores, an L x sources matrix.  L <= 32. */
 SS_API int32_t ss_recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int32_t L, int64_t s_begin,
                                  int64_t s_end, ss_ivec* idx_out, ss_mat* val_out);
 /* clean! [src/core.jl:478-484]: R[:,t] = -99 for every t with kt[t] == 0. */

@@ -470,9 +470,8 @@ int32_t ss_recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int32_
     SS_REQUIRE(L >= 1 && L <= 32 && L <= Y->cols, "ss_recommend_topl: L must be in 1..min(32, targets)");
     SS_REQUIRE(s_begin >= 0 && s_end <= Y->rows && s_begin <= s_end, "ss_recommend_topl: bad source range");
     SS_REQUIRE(idx_out->n == int64_t(L) * Y->rows, "ss_recommend_topl: idx_out must hold L x sources entries");
-    SS_REQUIRE(!val_out || (val_out->rows == L && val_out->cols == Y->rows && val_out->ld == L),
-               "ss_recommend_topl: val_out must be a dense L x sources matrix with ld == L");
-    SS_TRY(recommend_topl(ctx, Y, YT, L, s_begin, s_end, idx_out->d, val_out ? val_out->d : nullptr));
+    SS_REQUIRE(!val_out || (val_out->rows == L && val_out->cols == Y->rows), "ss_recommend_topl: val_out must be an L x sources matrix");
+    SS_TRY(recommend_topl(ctx, Y, YT, L, s_begin, s_end, idx_out->d, val_out ? val_out->d : nullptr, val_out ? val_out->ld : 0));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }

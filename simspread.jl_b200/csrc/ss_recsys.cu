@@ -184,7 +184,8 @@ __device__ __forceinline__ void list_insert_ordered(uint64_t& lkey, int32_t& lid
 
 __global__ void __launch_bounds__(256)
     rec_merge_kernel(const RecParams p, int L, int nwarp_chunks, const uint64_t* __restrict__ cand_key,
-                     const int32_t* __restrict__ cand_idx, int32_t* __restrict__ idx_out, double* __restrict__ val_out) {
+                     const int32_t* __restrict__ cand_idx, int32_t* __restrict__ idx_out, double* __restrict__ val_out,
+                     int64_t ldv) {
     __shared__ uint64_t skey[8][32];
     __shared__ int32_t sidx[8][32];
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256)
     }
     if (lane < L) {
         idx_out[s * L + lane] = (lane < cnt) ? lidx : -1;
-        if (val_out) val_out[s * L + lane] = (lane < cnt) ? rk_key_to_value(lkey) : 0.0;
+        if (val_out) val_out[s * ldv + lane] = (lane < cnt) ? rk_key_to_value(lkey) : 0.0;
     }
 }
 
@@ -248,6 +249,7 @@ struct FusedParams {
     int L;
     int32_t* idx_out;
     double* val_out;
+    int64_t ldv;          // leading dimension of val_out (>= L)
     int32_t* redo_cnt;
     int32_t* redo_list;
 };
@@ -482,12 +484,12 @@ __global__ void __launch_bounds__(FU_TPB, 1024 / FU_TPB) rec_fused_kernel(const 
                     }
                     if (rank < L) {
                         p.idx_out[s * L + rank] = mc;
-                        if (p.val_out) p.val_out[s * L + rank] = rk_key_to_value(my);
+                        if (p.val_out) p.val_out[s * p.ldv + rank] = rk_key_to_value(my);
                     }
                 }
                 if (tid >= n && tid < L) {  // fewer entries than L (cannot happen for L <= targets)
                     p.idx_out[s * L + tid] = -1;
-                    if (p.val_out) p.val_out[s * L + tid] = 0.0;
+                    if (p.val_out) p.val_out[s * p.ldv + tid] = 0.0;
                 }
             }
             __syncthreads();
@@ -505,7 +507,7 @@ namespace {
 
 // group kernels (expand / extract / merge) over the sources slist[0..count) or [s_begin, s_end)
 int32_t recommend_groups(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
-                         const int32_t* slist, int32_t* idx_out, double* val_out) {
+                         const int32_t* slist, int32_t* idx_out, double* val_out, int64_t ldv) {
     const int64_t nt = Y->cols;
     const int64_t ldacc = round_up(nt, 32);
     int64_t G = (int64_t(32) << 20) / (ldacc * 8);  // 3 concurrent groups x 32 MB of accumulators stay in L2
@@ -558,7 +560,7 @@ int32_t recommend_groups(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, 
         rec_expand_kernel<<<dim3(unsigned(q.G), EX_SLICES), EX_TPB, 0, streams[b]>>>(q);
         rec_extract_kernel<<<dim3(unsigned(ceil_div(nwc, 8)), unsigned(q.G)), 256, 0, streams[b]>>>(q, L, cpw, int(nwc),
                                                                                                   ckeys[b], cidxs[b]);
-        rec_merge_kernel<<<unsigned(q.G), 256, 0, streams[b]>>>(q, L, int(nwc), ckeys[b], cidxs[b], idx_out, val_out);
+        rec_merge_kernel<<<unsigned(q.G), 256, 0, streams[b]>>>(q, L, int(nwc), ckeys[b], cidxs[b], idx_out, val_out, ldv);
         ctx->launches += 3;
     }
     for (int i = 1; i < NS; ++i) {  // join the helper streams back into the context stream
@@ -644,11 +646,11 @@ int32_t launch_fused(ss_ctx* ctx, FusedParams& fp, int64_t ldacc, int64_t nsrc, 
 
 // top-L targets of every source of the 2-layer graph Y (CSR) / Y' (CSR), sources [s_begin, s_end)
 int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
-                       int32_t* idx_out, double* val_out) {
+                       int32_t* idx_out, double* val_out, int64_t ldv) {
     const int64_t nt = Y->cols;
     if (s_end <= s_begin || nt == 0) return SS_OK;
     const char* mode = getenv("SS_RECSYS_MODE");  // "groups": force the three-kernel form (debugging / A-B runs)
-    if (mode && !strcmp(mode, "groups")) return recommend_groups(ctx, Y, YT, L, s_begin, s_end, nullptr, idx_out, val_out);
+    if (mode && !strcmp(mode, "groups")) return recommend_groups(ctx, Y, YT, L, s_begin, s_end, nullptr, idx_out, val_out, ldv);
     const bool weighted = Y->values != nullptr;
     const int64_t ldacc = round_up(nt, 32);
     FusedParams fp{};
@@ -666,6 +668,7 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
     fp.L = L;
     fp.idx_out = idx_out;
     fp.val_out = val_out;
+    fp.ldv = ldv;
     // cluster shape: "8x1024" (default) = 8 CTAs of 1024 threads, one per SM (portable cluster size; 15 clusters =
     // 120 SMs co-resident on B200); "16x512" = 16 CTAs of 512 threads, two CTAs per SM (non-portable size; 14
     // clusters on B200, measured 3 % slower: the kernel is bound by the RED issue rate of the SMs it covers)
@@ -686,7 +689,7 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
     int32_t redo = 0;  // sources whose candidate list overflowed take the three-kernel form
     SS_CHECK_CUDA(cudaMemcpyAsync(&redo, fp.redo_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (redo > 0) SS_TRY(recommend_groups(ctx, Y, YT, L, 0, redo, fp.redo_list, idx_out, val_out));
+    if (redo > 0) SS_TRY(recommend_groups(ctx, Y, YT, L, 0, redo, fp.redo_list, idx_out, val_out, ldv));
     return SS_OK;
 }
 

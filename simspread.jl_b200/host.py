@@ -1078,12 +1078,7 @@ def recommend_topl(y, L: int = 20, weighted: Optional[bool] = None, s_range: Opt
     cyt = DCsr.from_dense(ctx, d, tiny if not weighted else float("-inf"), weighted, by_columns=True)
     idx = DIVec(ctx, L * ns)
     val = DMat(ctx, L, ns)
-    _, _, ldv, _ = val.info()
     b, e = s_range if s_range is not None else (0, ns)
-    if ldv == L:
-        check(lib().ss_recommend_topl(ctx.h, cy.h, cyt.h, int(L), int(b), int(e), idx.h, val.h))
-        v = val.to_host().T
-    else:  # L not a multiple of the 16-element row padding: indices only, scores re-read by the caller
-        check(lib().ss_recommend_topl(ctx.h, cy.h, cyt.h, int(L), int(b), int(e), idx.h, None))
-        v = None
+    check(lib().ss_recommend_topl(ctx.h, cy.h, cyt.h, int(L), int(b), int(e), idx.h, val.h))
+    v = val.to_host().T
     return idx.to_host().reshape(ns, L), v

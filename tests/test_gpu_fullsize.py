@@ -1,0 +1,208 @@
+"""`-m gpu` tests at BASELINE.json's FULL sizes, where the oracle cannot run: the CUDA path is checked through
+size-independent properties of the domain -- checksums of checksums (row / column sums of a product are products of
+sums: the linearity of predict in its operands), resource conservation of the spreading step, idempotence of the
+threshold, degree sum rules, determinism of row slabs, sortedness and permutation invariance of the ranking
+metrics -- plus sampled entries recomputed independently with torch (FP64) at the north-star tolerance.
+
+Inputs are generated on the device (they do not fit the host comfortably); torch is the checker here, never the
+thing measured.  Tolerance for FP64 scores: 1e-12 relative (north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import simspread_b200 as ss
+    from simspread_b200._lib import check
+    ss.build()
+    ctx = ss.Context.default()
+    dev = torch.device("cuda", ctx.device)
+    free, total = torch.cuda.mem_get_info(dev)
+    return {"ss": ss, "check": check, "ctx": ctx, "torch": torch, "dev": dev, "L": ss.lib(), "free_gb": free / 2**30}
+
+
+def colmajor(torch, rows, cols, dev):
+    ld = (rows + 15) // 16 * 16
+    return torch.zeros((cols, ld), dtype=torch.float64, device=dev), ld
+
+
+def fill(torch, buf, rows, seed, kind, p=0.05):
+    g = torch.Generator(device=buf.device)
+    g.manual_seed(seed)
+    step = max(1, (1 << 27) // buf.shape[1])
+    for c0 in range(0, buf.shape[0], step):
+        blk = buf[c0:c0 + step, :rows]
+        u = torch.rand(blk.shape, generator=g, device=buf.device, dtype=torch.float64)
+        blk.copy_(torch.round(u * 1e6) / 1e6 if kind == "uniform6" else (u < p).to(torch.float64))
+
+
+def relmax(torch, got, want):
+    return float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item())
+
+
+def test_c4_full_size_chain_properties(env):
+    """BASELINE config 4 (100k queries x 20k sources/features x 50k targets, FP64): spread + predict + clean!."""
+    ss, check, ctx, torch, dev, L = (env[k] for k in ("ss", "check", "ctx", "torch", "dev", "L"))
+    if env["free_gb"] < 120:
+        pytest.skip("needs ~100 GB of device memory")
+    nq, ns, nf, nt = 100_000, 20_000, 20_000, 50_000
+    bXq, ldq = colmajor(torch, nq, nf, dev)
+    bXs, lds = colmajor(torch, ns, nf, dev)
+    bY, ldy = colmajor(torch, ns, nt, dev)
+    bR, ldr = colmajor(torch, nq, nt, dev)
+    fill(torch, bXq, nq, 1, "uniform6")
+    fill(torch, bXs, ns, 2, "uniform6")
+    fill(torch, bY, ns, 3, "bernoulli", 0.05)
+    bY[7, :] = 0.0      # a target nobody has: clean! must flag its column
+    bXs[:, 11] = 0.0    # a source without features (it still has targets)
+    bXs[13, :] = 0.0    # a feature nobody has: kf = 0 -> its row of T is 0, not NaN
+    mXq, mXs = ss.DMat.wrap(ctx, bXq.data_ptr(), nq, nf, ldq), ss.DMat.wrap(ctx, bXs.data_ptr(), ns, nf, lds)
+    mY, mR = ss.DMat.wrap(ctx, bY.data_ptr(), ns, nt, ldy), ss.DMat.wrap(ctx, bR.data_ptr(), nq, nt, ldr)
+    kt = ss.DIVec(ctx, nt)
+    check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, ss._lib.SS_PREDICT_CLEAN, kt.h))
+    torch.cuda.synchronize()
+    Xq, Xs, Y, R = bXq[:, :nq], bXs[:, :ns], bY[:, :ns], bR[:, :nq]  # torch views, TRANSPOSED (row = column of the matrix)
+    # degrees: independent recount, and the sum rules sum(ks) = sum(kf) + sum(kt) = nnz(Xs) + nnz(Y)
+    ks_ = (Xs != 0).sum(0) + (Y != 0).sum(0)
+    kf_ = (Xs != 0).sum(1)
+    kt_ = (Y != 0).sum(1)
+    assert np.array_equal(kt.to_host(), kt_.cpu().numpy().astype(np.int32))
+    assert int(ks_.sum()) == int(kf_.sum()) + int(kt_.sum())
+    assert int(kt_[7]) == 0 and int(kf_[13]) == 0
+    # clean!: exactly the columns of degree-0 targets are -99, everything else is a finite non-negative score
+    flagged = (R == -99.0).all(1)
+    assert bool(torch.equal(flagged, kt_ == 0)) and int(flagged.sum()) >= 1
+    assert bool(torch.isfinite(R).all()) and float(R.amin(1)[~flagged].min()) >= 0.0
+    livemask = (~flagged).to(torch.float64)
+    # checksum of checksums (linearity): with w[s] = 1/ks[s], a[f] = 1/kf[f] (0 where the degree is 0)
+    #   row sums    R 1 = Xq (T 1),          T 1 = a .* (Xs' (w .* (Y 1)))           (over the live targets)
+    #   column sums 1' R = (1' Xq) T  ->  checked for a sample of columns through T's definition
+    w = torch.where(ks_ > 0, 1.0 / ks_.to(torch.float64), torch.zeros(ns, dtype=torch.float64, device=dev))
+    a = torch.where(kf_ > 0, 1.0 / kf_.to(torch.float64), torch.zeros(nf, dtype=torch.float64, device=dev))
+    y1 = torch.mv(Y.T, livemask)                   # Y 1 over live targets (length ns)
+    t1 = a * torch.mv(Xs, w * y1)                  # T 1 (length nf); Xs view is (nf, ns) = Xs'
+    want_rows = torch.mv(Xq.T, t1)                 # Xq (T 1)
+    got_rows = torch.mv(R.T, livemask)             # R 1 over the live targets, no 40 GB temporary
+    assert relmax(torch, got_rows, want_rows) < 5e-12  # sums of 5e4 non-negative terms, two summation orders
+    xq1 = Xq.sum(1)                                # 1' Xq (length nf)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(5)
+    cols = torch.randint(0, nt, (48,), generator=g).to(dev)
+    cols = cols[~flagged[cols]]
+    Tc = a[:, None] * (Xs @ (w[:, None] * Y[cols].T))   # T[:, cols]  (nf x 48), torch / cuBLAS FP64
+    assert relmax(torch, R[cols].sum(1), xq1 @ Tc) < 5e-12
+    # sampled entries recomputed independently: R[q, t] = Xq[q, :] . T[:, t]
+    rows = torch.randint(0, nq, (cols.numel(),), generator=g).to(dev)
+    want = (Xq[:, rows] * Tc).sum(0)
+    assert relmax(torch, R[cols, rows], want) < RTOL
+    # resource conservation of one spreading step: every source with neighbours hands on exactly its resource,
+    # sum_t Wst[s, t] = ky[s] / ks[s]  -> sum over the T built from it: sum_f kf[f] T[f, t] = sum_s (Xs 1)[s] w[s] Y[s, t]
+    lhs = (kf_.to(torch.float64)[:, None] * Tc).sum(0)
+    rhs = ((Xs.sum(0) * w)[:, None] * Y[cols].T).sum(0)
+    assert relmax(torch, lhs, rhs) < 5e-12
+    # determinism / slab independence: the first 1000 query rows computed on their own are bit-identical
+    bR2, ldr2 = colmajor(torch, 1000, nt, dev)
+    mXq2 = ss.DMat.wrap(ctx, bXq.data_ptr(), 1000, nf, ldq)
+    mR2 = ss.DMat.wrap(ctx, bR2.data_ptr(), 1000, nt, ldr2)
+    check(L.ss_predict_query(ctx.h, mXq2.h, mXs.h, mY.h, mR2.h, ss._lib.SS_PREDICT_CLEAN, None))
+    torch.cuda.synchronize()
+    assert bool(torch.equal(bR2[:, :1000], R[:, :1000]))
+
+
+def test_c4_full_size_featurize_degrees_csr(env):
+    """The threshold / degree / CSR kernels on the C4-sized similarity block (120k x 20k, 19 GB)."""
+    ss, check, ctx, torch, dev, L = (env[k] for k in ("ss", "check", "ctx", "torch", "dev", "L"))
+    if env["free_gb"] < 80:
+        pytest.skip("needs ~60 GB of device memory")
+    n, m, alpha = 120_000, 20_000, 0.93
+    bS, ld = colmajor(torch, n, m, dev)
+    fill(torch, bS, n, 9, "uniform6")
+    bS[3, 5] = float("nan")   # NaN >= alpha is false -> 0
+    bS[4, 6] = alpha          # inclusive threshold
+    bX, _ = colmajor(torch, n, m, dev)
+    mS, mX = ss.DMat.wrap(ctx, bS.data_ptr(), n, m, ld), ss.DMat.wrap(ctx, bX.data_ptr(), n, m, ld)
+    check(L.ss_featurize(ctx.h, mS.h, alpha, 1, mX.h))
+    torch.cuda.synchronize()
+    S, X = bS[:, :n], bX[:, :n]
+    keep = S >= alpha
+    assert bool(torch.equal(X != 0, keep)) and float(X[3, 5]) == 0.0 and float(X[4, 6]) == alpha
+    assert bool(torch.equal(X[keep], S[keep]))               # weighted: kept entries unchanged, bit for bit
+    check(L.ss_featurize(ctx.h, mX.h, alpha, 1, mX.h))          # idempotent (featurize! in place)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(X[keep], S[keep])) and int((X != 0).sum()) == int(keep.sum())
+    # degrees of the featurized block: row / column counts against torch, and sum(rows) == sum(cols) == nnz
+    kr, kc = ss.DIVec(ctx, n), ss.DIVec(ctx, m)
+    check(L.ss_degrees(ctx.h, None, mX.h, kr.h, None, kc.h))   # row and column non-zero counts of the block
+    krh, kch = kr.to_host().astype(np.int64), kc.to_host().astype(np.int64)
+    assert np.array_equal(krh, keep.sum(0).cpu().numpy()) and np.array_equal(kch, keep.sum(1).cpu().numpy())
+    assert krh.sum() == kch.sum() == int(keep.sum())
+    # CSR straight from the raw similarities: same edge count, row extents = row degrees, ascending columns
+    h = C.c_void_p()
+    check(L.ss_featurize_csr(ctx.h, mS.h, alpha, 1, C.byref(h)))
+    csr = ss.DCsr(ctx, h)
+    assert csr.nnz == int(keep.sum()) and (csr.rows, csr.cols) == (n, m)
+    rp, ci, va = csr.to_host()
+    assert np.array_equal(np.diff(rp.astype(np.int64)), krh)
+    inner = np.ones(csr.nnz, dtype=bool)
+    inner[rp[1:-1][rp[1:-1] < csr.nnz]] = False            # first entry of every row
+    assert np.all(np.diff(ci.astype(np.int64))[inner[1:]] > 0)
+    r0 = 77_777
+    assert np.array_equal(ci[rp[r0]:rp[r0 + 1]], np.flatnonzero(keep[:, r0].cpu().numpy()))
+    assert np.array_equal(va[rp[r0]:rp[r0 + 1]], S[:, r0][keep[:, r0]].cpu().numpy())
+
+
+def test_full_size_ranking_metric_properties(env):
+    """AuROC / AuPRC / top-L on 10^9 scores: invariance under a permutation of the pairs and under a strictly
+    increasing transform of the scores, the perfect / inverted rankings, sortedness of the top-L lists."""
+    ss, check, ctx, torch, dev, L = (env[k] for k in ("ss", "check", "ctx", "torch", "dev", "L"))
+    if env["free_gb"] < 80:
+        pytest.skip("needs ~50 GB of device memory")
+    M = 1_000_000_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(21)
+    sc = torch.round(torch.rand(M, dtype=torch.float64, device=dev, generator=g) * 1e7) / 1e7  # ~10^7 distinct values: ties
+    lb = (torch.rand(M, device=dev, generator=g) < 0.02 + 0.05 * sc).to(torch.uint8)
+
+    def auc(labels, scores):
+        out = (C.c_double * 2)()
+        torch.cuda.synchronize()
+        check(L.ss_auroc_auprc(ctx.h, C.c_void_p(labels.data_ptr()), C.c_void_p(scores.data_ptr()), scores.numel(), out))
+        return out[0], out[1]
+
+    base = auc(lb, sc)
+    assert 0.5 < base[0] < 1.0 and 0.0 < base[1] < 1.0
+    # a strictly increasing transform keeps every comparison: identical curve, bit for bit
+    assert auc(lb, sc * 3.0 + 1.0) == base
+    # reversing the order of the pairs changes nothing (ties are grouped by value, not by position)
+    assert auc(lb.flip(0).contiguous(), sc.flip(0).contiguous()) == pytest.approx(base, rel=1e-12)
+    del sc
+    # perfect and inverted rankings of the same labels
+    perfect = lb.to(torch.float64)
+    a_perf = auc(lb, perfect)
+    assert a_perf[0] == pytest.approx(1.0, rel=1e-12)
+    a_inv = auc(lb, 1.0 - perfect)
+    assert a_inv[0] == pytest.approx(0.0, abs=1e-12)
+    del perfect, lb
+    # top-L over a 100k x 5k score block: lists are sorted, hold the row maximum first, and no entry outside beats the last
+    rows, cols, Ltop = 100_000, 5_000, 20
+    bR, ldr = colmajor(torch, rows, cols, dev)
+    fill(torch, bR, rows, 31, "uniform6")
+    mR = ss.DMat.wrap(ctx, bR.data_ptr(), rows, cols, ldr)
+    idx = ss.DIVec(ctx, Ltop * rows)
+    check(L.ss_topl_rows(ctx.h, mR.h, Ltop, idx.h, None))
+    ih = torch.from_numpy(idx.to_host().reshape(rows, Ltop).astype(np.int64)).to(dev)
+    R = bR[:, :rows].T                                  # (rows, cols) view
+    vals = torch.gather(R, 1, ih)
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())
+    assert bool(torch.equal(vals[:, 0], R.max(1).values))
+    ties_in_order = (vals[:, :-1] > vals[:, 1:]) | (ih[:, :-1] < ih[:, 1:])   # equal scores: ascending column
+    assert bool(ties_in_order.all())
+    kth = torch.topk(R[:2000], Ltop, dim=1).values
+    assert bool(torch.equal(kth, vals[:2000]))
