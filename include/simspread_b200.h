@@ -58,9 +58,11 @@ extern "C" {
 #define SS_PRECISION_F64 0u
 #define SS_PRECISION_TF32 (1u << 4)
 /* FP64-grade results from exact INT8 tensor-core products (Ozaki-style 8-bit slicing of non-negative
- * operands, INT32 accumulation in TMEM, FP64 recombination; csrc/ss_umma.cu).  The error bound is
- * normwise (~1e-13 of a typical entry with the default 6 slices at K = 20000), not element-wise,
- * so the mode is opt-in; SS_INT8_SLICES=4..8 in the environment changes the slice count. */
+ * operands, INT32 accumulation in TMEM, FP64 recombination; csrc/ss_umma.cu).  The a-priori error bound is
+ * normwise (K * (S + 1.5) * 2^(-8S) * rowmax * colmax), so every entry is CERTIFIED a posteriori in the epilogue
+ * (bound <= 4e-13 * entry, or the entry is an exact 0); a product with an uncertified entry is re-run on the FP64
+ * DMMA path (ss_ctx_int8_stats).  SS_INT8_SLICES=4..8 changes the slice count (default 6), SS_INT8_TOL the
+ * certificate, SS_INT8_CERTIFY=0 disables it. */
 #define SS_PRECISION_F64_INT8 (3u << 4)
 #define SS_PRECISION_MASK (15u << 4)
 
@@ -84,6 +86,9 @@ SS_API int32_t ss_ctx_sync(ss_ctx* ctx);
 SS_API int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out);
 /* number of kernels launched on this context since creation (bench.py's gpu_launches) */
 SS_API int32_t ss_ctx_launch_count(ss_ctx* ctx, int64_t* count);
+/* SS_PRECISION_F64_INT8 bookkeeping: stats3 = {products computed on the INT8 tensor pipe, products whose a-posteriori
+ * certificate failed and that were re-run on the FP64 DMMA path, entries that failed in the last product}. */
+SS_API int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats3);
 /* Per-kernel device timing of the chain-product GEMMs (CUDA events on the context stream, recorded
  * around each launch while enabled).  ss_ctx_profile_read() synchronises, returns up to `cap`
  * (milliseconds, algorithmic flops = 2*M*N*K) pairs in launch order and clears the list. */

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ss_ctx_sync": (c_i32, [vp]),
     "ss_ctx_stream": (c_i32, [vp, P(vp)]),
     "ss_ctx_launch_count": (c_i32, [vp, P(c_i64)]),
+    "ss_ctx_int8_stats": (c_i32, [vp, vp]),
     "ss_ctx_profile": (c_i32, [vp, c_i32]),
     "ss_ctx_profile_read": (c_i32, [vp, P(c_f64), P(c_f64), c_i32, P(c_i32)]),
     "ss_host_alloc": (c_i32, [c_i64, P(vp)]),

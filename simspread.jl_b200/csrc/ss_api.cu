@@ -124,6 +124,12 @@ int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out) {
     return SS_OK;
 }
 
+int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats3) {
+    SS_REQUIRE(ctx && stats3, "ss_ctx_int8_stats: null argument");
+    for (int i = 0; i < 3; ++i) stats3[i] = ctx->int8_stats[i];
+    return SS_OK;
+}
+
 int32_t ss_ctx_launch_count(ss_ctx* ctx, int64_t* count) {
     SS_REQUIRE(ctx && count, "ss_ctx_launch_count: null argument");
     *count = ctx->launches;
@@ -571,7 +577,26 @@ static int32_t chain_gemm(ss_ctx* ctx, uint32_t precision, int opA, const double
             const int v = atoi(env);
             if (v >= 2 && v <= 8) S = v;
         }
-        return launch_gemm_i8(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, S);
+        // every entry is certified a posteriori (error bound <= tol * entry, default 4e-13 so that the two
+        // products of a chain stay below 1e-12); a product with uncertified entries is re-run on the FP64 DMMA
+        // path.  SS_INT8_CERTIFY=0 skips the check, SS_INT8_TOL overrides the tolerance.
+        double tol = 4e-13;
+        if (const char* env = getenv("SS_INT8_TOL")) {
+            const double v = atof(env);
+            if (v > 0.0) tol = v;
+        }
+        const char* ce = getenv("SS_INT8_CERTIFY");
+        const bool certify = !(ce && ce[0] == '0');
+        int64_t bad = 0;
+        SS_TRY(launch_gemm_i8(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, S, certify ? tol : 0.0,
+                              certify ? &bad : nullptr));
+        ctx->int8_stats[0] += 1;
+        ctx->int8_stats[2] = bad;
+        if (bad > 0) {
+            ctx->int8_stats[1] += 1;
+            return launch_gemm_f64(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
+        }
+        return SS_OK;
     }
     set_error("unknown precision flag 0x%x", precision);
     return SS_ERR_INVALID;

@@ -54,6 +54,9 @@ struct ss_ctx {
     cudaStream_t copy_in = nullptr;  // H2D pipeline
     cudaStream_t copy_out = nullptr; // D2H pipeline
     int64_t launches = 0;
+    // int8-sliced products since context creation: {products, products re-run on the DMMA path, entries that
+    // failed the certificate in the last product}
+    int64_t int8_stats[3] = {0, 0, 0};
     // workspaces reused across predict calls (never shrink)
     ss::Scratch ws[16];
     int32_t* tile_counter = nullptr;
@@ -115,7 +118,7 @@ int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, con
                          bool split);
 int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                        int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
-                       int S);
+                       int S, double cert_tol, int64_t* uncertified);
 int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr* XsT, const ss_mat* Y, ss_mat* R, uint32_t flags,

@@ -71,6 +71,11 @@ struct UmmaParams {
     const double* rscale;  // integer mode: 2^ea[m]
     const double* cscale;  // integer mode: 2^eb[n]
     int* sync_prog;        // loose lockstep of the producers (see ss_gemm.cu), optional
+    // integer mode, a-posteriori certificate: an entry passes if acc >= cert * 2^ea[m] * 2^eb[n] (its absolute
+    // error bound is then <= tol * acc) or if it is exactly 0 and no operand entry was truncated to 0
+    double cert;
+    int zero_ok;
+    unsigned long long* cert_fail;  // number of entries that did not pass (null: no check)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -249,7 +254,8 @@ __global__ void __launch_bounds__(U_THREADS, 1)
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
-              for (int g = 0; g < p.ngroups; ++g, ++it) {
+              unsigned nfail = 0;
+            for (int g = 0; g < p.ngroups; ++g, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // epilogue has drained this accumulator
@@ -295,6 +301,7 @@ __global__ void __launch_bounds__(U_THREADS, 1)
                 }
                 if (KIND == 1) rs = __ldg(p.rscale + row);
             }
+            unsigned nfail = 0;
             for (int g = 0; g < p.ngroups; ++g, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -322,6 +329,10 @@ __global__ void __launch_bounds__(U_THREADS, 1)
                                     if (!first) v += *dst;
                                 }
                                 if (last) {
+                                    if (KIND == 1 && p.cert_fail) {
+                                        const bool pass = (v >= p.cert * rs * __ldg(p.cscale + col)) || (v == 0.0 && p.zero_ok);
+                                        nfail += pass ? 0u : 1u;
+                                    }
                                     if (p.row_div) v = zero_row ? 0.0 : v / inv;
                                     if (p.col_flag && __ldg(p.col_flag + col) == 0) v = -99.0;
                                 }
@@ -333,6 +344,10 @@ __global__ void __launch_bounds__(U_THREADS, 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            }
+            if (KIND == 1 && p.cert_fail) {
+                nfail = __reduce_add_sync(0xffffffffu, nfail);
+                if (lane == 0 && nfail) atomicAdd(p.cert_fail, (unsigned long long)nfail);
             }
         }
     }
@@ -483,7 +498,8 @@ __global__ void __launch_bounds__(256)
 
 // r in [0,1) -> S unsigned 8-bit digits, most significant first (all operations exact)
 template <int DUMMY = 0>
-__device__ __forceinline__ void slice_digits(double r, int S, uint8_t* out, int64_t plane) {
+__device__ __forceinline__ void slice_digits(double r, int S, uint8_t* out, int64_t plane, int* flags) {
+    if (r != 0.0 && r < ldexp(1.0, -8 * S)) atomicOr(flags, 4);  // a non-zero entry whose digits are all 0
     for (int i = 0; i < S; ++i) {
         r *= 256.0;
         const double q = floor(r);
@@ -495,20 +511,20 @@ __device__ __forceinline__ void slice_digits(double r, int S, uint8_t* out, int6
 // k-contiguous source -> planes[i][j*kp + k]
 __global__ void __launch_bounds__(256)
     slice_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, const double* __restrict__ scale,
-                        int S, uint8_t* __restrict__ planes, int64_t kp) {
+                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags) {
     const int64_t k = int64_t(blockIdx.x) * 256 + threadIdx.x;
     if (k >= kp) return;
     const int64_t plane = J * kp;
     for (int64_t j = blockIdx.y; j < J; j += gridDim.y) {
         const double x = (k < K) ? src[j * ld + k] : 0.0;
-        slice_digits(fabs(x) / scale[j], S, planes + j * kp + k, plane);  // scale is a power of two: exact
+        slice_digits(fabs(x) / scale[j], S, planes + j * kp + k, plane, flags);  // scale is a power of two: exact
     }
 }
 
 // m-contiguous source -> planes[i][m*kp + k] (32x32 transpose through shared memory)
 __global__ void __launch_bounds__(256)
     slice_mmajor_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, const double* __restrict__ scale,
-                        int S, uint8_t* __restrict__ planes, int64_t kp) {
+                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t m0 = int64_t(blockIdx.x) * 32, k0 = int64_t(blockIdx.y) * 32;
@@ -522,7 +538,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = ty; j < 32; j += 8) {
         const int64_t m = m0 + j, k = k0 + tx;
-        if (m < M && k < kp) slice_digits(fabs(tile[tx][j]) / scale[m], S, planes + m * kp + k, plane);
+        if (m < M && k < kp) slice_digits(fabs(tile[tx][j]) / scale[m], S, planes + m * kp + k, plane, flags);
     }
 }
 
@@ -629,7 +645,7 @@ int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, con
 // S = number of 8-bit slices per operand (4..8).
 int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                        int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
-                       int S) {
+                       int S, double cert_tol, int64_t* uncertified) {
     SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8: empty problem");
     SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_i8: dimension too large");
     SS_REQUIRE(S >= 2 && S <= MAXS, "gemm_i8: 2..%d slices", MAXS);
@@ -645,31 +661,32 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
     uint8_t* Bp = static_cast<uint8_t*>(p);
     double* cs = reinterpret_cast<double*>(Bp + size_t(S) * N * kp);
     int* flags = reinterpret_cast<int*>(cs + N);
-    SS_CHECK_CUDA(cudaMemsetAsync(flags, 0, 4, ctx->stream));
+    unsigned long long* cert_fail = reinterpret_cast<unsigned long long*>(flags + 2);
+    SS_CHECK_CUDA(cudaMemsetAsync(flags, 0, 16, ctx->stream));
     const int rgrid = ctx->sm_count * 8;
     if (opA == SS_OP_N) {
         rowscale_mmajor_kernel<<<unsigned(ceil_div(M, 256)), 256, 0, ctx->stream>>>(A, M, K, lda, rs, flags);
         dim3 g{unsigned(ceil_div(M, 32)), unsigned(ceil_div(kp, 32))};
         SS_REQUIRE(g.y <= 65535, "gemm_i8: K too large for the transpose grid");
-        slice_mmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, rs, S, Ap, kp);
+        slice_mmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, rs, S, Ap, kp, flags);
     } else {
         rowscale_kmajor_kernel<<<unsigned(M < rgrid ? M : rgrid), 256, 0, ctx->stream>>>(A, K, M, lda, rs, flags);
         const int64_t gx = ceil_div(kp, 256);
         dim3 g{unsigned(gx), grid_y_for(ctx, gx, M)};
-        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, rs, S, Ap, kp);
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, rs, S, Ap, kp, flags);
     }
     {
         rowscale_kmajor_kernel<<<unsigned(N < rgrid ? N : rgrid), 256, 0, ctx->stream>>>(B, K, N, ldb, cs, flags);
         const int64_t gx = ceil_div(kp, 256);
         dim3 g{unsigned(gx), grid_y_for(ctx, gx, N)};
-        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, cs, S, Bp, kp);
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, cs, S, Bp, kp, flags);
     }
     ctx->launches += 4;
     SS_CHECK_CUDA(cudaGetLastError());
     int hflags = 0;
     SS_CHECK_CUDA(cudaMemcpyAsync(&hflags, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (hflags) {
+    if (hflags & 3) {
         set_error("the int8-sliced precision mode needs finite, non-negative operands (%s entry found); "
                   "use the default FP64 mode", (hflags & 2) ? "NaN/Inf" : "negative");
         return SS_ERR_UNSUPPORTED;
@@ -720,7 +737,22 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
     q.col_flag = col_flag;
     q.rscale = rs;
     q.cscale = cs;
-    return launch_umma<1>(ctx, maps, q, 2.0 * double(M) * double(N) * double(K));
+    // A-posteriori certificate.  With x = 2^e sum_i q_i 2^(-8i) + d, 0 <= d < 2^(e-8S) (truncation) and the slice pairs
+    // with i + j > S + 1 dropped (each < 2^(16-8(i+j))), the absolute error of an entry is below
+    // K * (S + 1.5) * 2^(-8S) * 2^ea[m] * 2^eb[n]; it is <= tol * entry as soon as entry >= cert * 2^ea * 2^eb.
+    const bool certify = uncertified != nullptr && cert_tol > 0.0;
+    q.cert = certify ? double(K) * (double(S) + 1.5) * ldexp(1.0, -8 * S) / cert_tol : 0.0;
+    q.zero_ok = (hflags & 4) ? 0 : 1;
+    q.cert_fail = certify ? cert_fail : nullptr;
+    SS_TRY(launch_umma<1>(ctx, maps, q, 2.0 * double(M) * double(N) * double(K)));
+    if (uncertified) *uncertified = 0;
+    if (certify) {
+        unsigned long long h = 0;
+        SS_CHECK_CUDA(cudaMemcpyAsync(&h, cert_fail, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        *uncertified = int64_t(h);
+    }
+    return SS_OK;
 }
 
 }  // namespace ss

@@ -57,6 +57,13 @@ class Context:
         check(lib().ss_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def int8_stats(self):
+        """(products on the INT8 tensor pipe, products re-run in FP64 after a failed certificate, entries that failed
+        in the last product) -- bookkeeping of precision="f64_int8"."""
+        out = (C.c_int64 * 3)()
+        check(lib().ss_ctx_int8_stats(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def profile(self, enable: bool):
         check(lib().ss_ctx_profile(self.h, int(enable)))
 

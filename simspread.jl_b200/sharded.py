@@ -295,8 +295,9 @@ def samplesort_auroc_auprc(backend, torch, dist, labels, scores, world: int, ran
     samp = torch.zeros(ns, dtype=torch.int64, device=dev)
     have = torch.tensor([min(ns, m)], dtype=torch.int64, device=dev)
     if m:
-        pos = torch.linspace(0, m - 1, steps=min(ns, m), device=dev).to(torch.int64)
-        samp[:pos.numel()] = keys[pos]
+        cnt = min(ns, m)  # integer arithmetic: a float32 linspace rounds past m - 1 for large m
+        pos = (torch.arange(cnt, dtype=torch.int64, device=dev) * (m - 1)) // max(cnt - 1, 1)
+        samp[:cnt] = keys[pos]
     all_s = [torch.zeros_like(samp) for _ in range(world)]
     all_n = [torch.zeros_like(have) for _ in range(world)]
     dist.all_gather(all_s, samp)

@@ -729,6 +729,55 @@ def test_gemm_f64_from_int8_slices(ss, M, N, K, op):
     assert st == 6 and b"non-negative" in ss.lib().ss_last_error()
 
 
+def test_int8_mode_certificate_and_fp64_fallback(ss):
+    """precision="f64_int8" certifies every entry a posteriori (error bound <= 4e-13 * entry, or an exact zero with no
+    operand entry truncated to zero).  Products that cannot be certified are re-run on the FP64 DMMA path, so the
+    result is within the FP64 tolerance either way; ss_ctx_int8_stats tells which path produced it."""
+    from simspread_b200._lib import SS_OP_N, SS_PRECISION_F64_INT8, check
+    rng = np.random.default_rng(99)
+    ctx = ss.Context.default()
+    M, N, K = 200, 300, 4000
+
+    def run(A, B):
+        before = ctx.int8_stats()
+        dA, dB, dC = ss.DMat.from_host(ctx, A), ss.DMat.from_host(ctx, B), ss.DMat(ctx, A.shape[0], B.shape[1])
+        check(ss.lib().ss_gemm_lowp(ctx.h, SS_OP_N, dA.h, dB.h, dC.h, None, None, SS_PRECISION_F64_INT8))
+        after = ctx.int8_stats()
+        assert after[0] == before[0] + 1
+        want = (A.astype(np.longdouble) @ B.astype(np.longdouble)).astype(float)
+        got = dC.to_host()
+        assert np.array_equal(got == 0, want == 0)
+        nz = want != 0
+        assert np.max(np.abs(got[nz] - want[nz]) / want[nz]) < RTOL
+        return after[1] - before[1], after[2]
+
+    # (1) dense similarity-like operands: certified, no fallback
+    A, B = rng.random((M, K)), rng.random((K, N))
+    assert run(A, B) == (0, 0)
+    # (2) block structure: exact zeros (disjoint supports) are certified as zeros
+    A2, B2 = A.copy(), B.copy()
+    A2[:, K // 2:] = 0.0
+    B2[:K // 2, :N // 2] = 0.0
+    assert run(A2, B2) == (0, 0)
+    # (3) one huge entry per row next to tiny ones: the normwise bound says nothing about the small entries of the
+    #     product -> the certificate fails -> FP64 fallback, result still within tolerance
+    A3 = rng.random((M, K)) * 1e-9
+    A3[:, 0] = 1.0
+    B3 = rng.random((K, N))
+    B3[0, :] = 0.0
+    fell_back, failed = run(A3, B3)
+    assert fell_back == 1 and failed > 0
+    # (4) an entry far below 2^-48 of its row maximum is truncated to 0: exact zeros can no longer be certified
+    A4, B4 = A2.copy(), B2.copy()
+    A4[5, 7] = 1e-30
+    fell_back, failed = run(A4, B4)
+    assert fell_back == 1 and failed > 0
+    # (5) the same entry with supports that overlap everywhere: nothing is zero, everything is large enough
+    A5 = A.copy()
+    A5[5, 7] = 1e-30
+    assert run(A5, B) == (0, 0)
+
+
 def test_predict_f64_int8_mode_against_oracle(ss, o):
     S, Yfull = _enzyme_like(o, seed=6)
     N, Nt = Yfull.shape
