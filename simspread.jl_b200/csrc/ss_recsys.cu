@@ -261,14 +261,6 @@ __device__ __forceinline__ int hi_image(double v) {
     return hi ^ ((hi >> 31) & 0x7fffffff);
 }
 
-__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const uint64_t w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w > v ? w : v;
-    }
-    return v;
-}
 
 // FU_C CTAs per cluster (launch attribute), FU_TPB threads per CTA, 1024 / FU_TPB CTAs per SM: with two
 // CTAs of different clusters on one SM the select / zero phases of one source overlap the RED stream of another.
@@ -680,6 +672,8 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
 #define SS_FUSED(C_, T_, U_) (weighted ? launch_fused<true, C_, T_, U_>(ctx, fp, ldacc, nsrc, &ncl) : launch_fused<false, C_, T_, U_>(ctx, fp, ldacc, nsrc, &ncl))
     if (shape && !strcmp(shape, "16x512")) st = SS_FUSED(16, 512, 16);
     else if (shape && !strcmp(shape, "8x512")) st = SS_FUSED(8, 512, 16);
+    else if (shape && !strcmp(shape, "6x1024")) st = SS_FUSED(6, 1024, 16);
+    else if (shape && !strcmp(shape, "7x1024")) st = SS_FUSED(7, 1024, 16);
     else if (unit == 8) st = SS_FUSED(8, 1024, 8);
     else st = SS_FUSED(8, 1024, 16);
 #undef SS_FUSED
