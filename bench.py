@@ -45,6 +45,9 @@ def parse_args():
                     "a scaled run is not a bench value)")
     ap.add_argument("--precision", choices=["f64", "tf32", "f64_int8"], default="f64",
                     help="opt-in reduced-precision chain on tcgen05 (not the BASELINE metric; N=1 only)")
+    ap.add_argument("--reference-workload", choices=["C4", "C2", "C3"], default="C4",
+                    help="with --impl reference: which BASELINE config the CPU restatement is timed on (C4 = the bench "
+                         "workload; C2 / C3 are the side measurements quoted in DESIGN.md)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -113,9 +116,54 @@ def cpu_reference_run(steps: int, warmup: int, sample_div: int = 20):
     }, t
 
 
+def cpu_reference_small_configs(which: str):
+    """The reference's literal CPU path (dense n x n construct -> spread -> A*(W*W) -> clean!) on BASELINE config 2
+    (Enzyme-shaped, all 10 folds) or on ONE alpha of config 3 (n = 17 000; the dense DGEMMs do not depend on alpha)."""
+    import numpy as np
+    from oracle import simspread_oracle as o
+    rng = np.random.default_rng(20241)
+    if which == "C2":
+        N, Nt, alpha, weighted = 445, 664, 0.35, False
+        S = np.round(rng.beta(2, 5, size=(N, N)), 6)
+        np.fill_diagonal(S, 1.0)
+        Y = (rng.random((N, Nt)) < 0.0099).astype(float)
+        names = [f"D{i:04d}" for i in range(N)]
+        folds = o.split_round_robin([names[i] for i in rng.permutation(N)], 10)
+        nq_total = N
+    else:
+        nq, ns, Nt, alpha, weighted = 5000, 5000, 2000, 0.5, True
+        N = nq + ns
+        S = np.round(rng.random((N, N)), 6)
+        Y = (rng.random((N, Nt)) < 0.01).astype(float)
+        names = [f"n{i}" for i in range(N)]
+        folds = [names[:nq]]
+        nq_total = nq
+    tn = [f"t{j}" for j in range(Nt)]
+    t0 = time.perf_counter()
+    Xo, xr, xc = o.featurize(S, names, names, alpha, weighted)
+    n_full = 0
+    for q in folds:
+        Ao, Bo, nn = o.construct_queries(Y, (names, tn), Xo, (xr, xc), q)
+        w = o.predict_dense(Ao, Bo, nn, q, tn)
+        o.clean(w, Ao, nn, tn)
+        n_full = Ao.shape[0]
+    t = time.perf_counter() - t0
+    return {"value": nq_total * Nt / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{which}: literal NumPy/OpenBLAS restatement of featurize + construct + spread + A*(W*W) + clean!, "
+                      f"{len(folds)} fold(s), dense n = {n_full}", "seconds_per_step": t}, t
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return 0
+    if args.reference_workload != "C4":
+        base, t = cpu_reference_small_configs(args.reference_workload)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": t * 1e3, "higher_is_better": True, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": args.reference_workload}, "cpu_baseline": base,
+                          "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
         return 0
     base, t = cpu_reference_run(args.steps, args.warmup)
     line = {

@@ -1,6 +1,7 @@
 """Wall-clock of the other BASELINE configs through the public host API (they are parity-test cases,
 not the bench line): C2 = Enzyme-shaped 10-fold CV, C3 = 21-point alpha sweep on 5k queries x 2k
-targets.  The CPU oracle's literal path is timed on C2 (all folds) for scale.  Writes
+targets.  The reference's literal CPU path is timed beside them by `bench.py --impl reference
+--reference-workload C2|C3` (the only place outside tests/ that runs the oracle).  Writes
 gpurun_out/configs.json; run under gpurun."""
 import json
 import os
@@ -10,8 +11,17 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import subprocess
+
 import simspread_b200 as ss
-from oracle import simspread_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def reference_arm(workload):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reference-workload", workload],
+                       capture_output=True, text=True, check=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])
 
 out = {}
 rng = np.random.default_rng(20241)
@@ -29,14 +39,8 @@ for _ in range(5):
     res = ss.cross_validate(DT, DD, 0.35, weighted=False, k_=10, seed=1)
     ts.append(time.perf_counter() - t0)
 t_gpu = float(np.median(ts))
-folds = res["folds"]
-t0 = time.perf_counter()
-Xo, xr, xc = o.featurize(S, names, names, 0.35, False)
-for q in folds:
-    Ao, Bo, nn = o.construct_queries(Y, (names, tn), Xo, (xr, xc), q)
-    w = o.predict_dense(Ao, Bo, nn, q, tn)
-    o.clean(w, Ao, nn, tn)
-t_cpu = time.perf_counter() - t0
+ref2 = reference_arm("C2")
+t_cpu = ref2["cpu_baseline"]["seconds_per_step"]
 out["C2_enzyme_10fold_cv"] = {"shape": [N, Nt], "alpha": 0.35, "weighted": False, "gpu_wall_s_median_of_5": t_gpu,
                               "scores_per_s": N * Nt / t_gpu, "cpu_oracle_literal_wall_s": t_cpu,
                               "cpu_cores": os.cpu_count(), "AuROC": res["AuROC"], "AuPRC": res["AuPRC"],
@@ -67,16 +71,11 @@ print(json.dumps({k: v for k, v in out["C3_alpha_sweep_21_points"].items() if k 
 # proxy for the reference's `GPU=true` cuBLAS SGEMM path (src/core.jl:404-419), at the C2 and C3 sizes.
 if os.environ.get("SS_SKIP_REFERENCE_FORMS") != "1":
     import torch
-    t0 = time.perf_counter()
-    Xo, xr, xc = o.featurize(S3, n3, n3, 0.5, True)
-    Ao, Bo, nn = o.construct_queries(Y3, (n3, t3), Xo, (xr, xc), n3[:nq])
-    w = o.predict_dense(Ao, Bo, nn, n3[:nq], t3)
-    o.clean(w, Ao, nn, t3)
-    t_cpu3 = time.perf_counter() - t0
-    n_full = Ao.shape[0]
-    del Ao, Bo, Xo
-    out["C3_cpu_literal_one_alpha"] = {"alpha": 0.5, "n": n_full, "wall_s": t_cpu3, "scores_per_s": nq * nt / t_cpu3,
-                                       "cores": os.cpu_count(), "kind": "NumPy/OpenBLAS restatement of the reference CPU path (not Julia)"}
+    ref3 = reference_arm("C3")
+    out["C3_cpu_literal_one_alpha"] = {"alpha": 0.5, "wall_s": ref3["cpu_baseline"]["seconds_per_step"],
+                                       "scores_per_s": ref3["value"], "cores": ref3["cpu_baseline"]["cores"],
+                                       "sample": ref3["cpu_baseline"]["sample"],
+                                       "kind": "NumPy/OpenBLAS restatement of the reference CPU path (not Julia)"}
     print(json.dumps(out["C3_cpu_literal_one_alpha"]), flush=True)
     proxy = {}
     for label, n_ in (("C2_fold_n1510", 1510), ("C3_n17000", 17000)):
