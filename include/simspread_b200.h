@@ -86,9 +86,10 @@ SS_API int32_t ss_ctx_sync(ss_ctx* ctx);
 SS_API int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out);
 /* number of kernels launched on this context since creation (bench.py's gpu_launches) */
 SS_API int32_t ss_ctx_launch_count(ss_ctx* ctx, int64_t* count);
-/* SS_PRECISION_F64_INT8 bookkeeping: stats3 = {products computed on the INT8 tensor pipe, products whose a-posteriori
- * certificate failed and that were re-run on the FP64 DMMA path, entries that failed in the last product}. */
-SS_API int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats3);
+/* SS_PRECISION_F64_INT8 bookkeeping: stats4 = {products computed on the INT8 tensor pipe, products whose a-posteriori
+ * certificate failed and that were re-run on the FP64 DMMA path, entries that failed in the last product, slice pairs
+ * of the last product (planes that hold only zeros are skipped: a 0/1 matrix is one plane)}. */
+SS_API int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats4);
 /* Per-kernel device timing of the chain-product GEMMs (CUDA events on the context stream, recorded
  * around each launch while enabled).  ss_ctx_profile_read() synchronises, returns up to `cap`
  * (milliseconds, algorithmic flops = 2*M*N*K) pairs in launch order and clears the list. */

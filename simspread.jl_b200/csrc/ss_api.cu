@@ -124,9 +124,10 @@ int32_t ss_ctx_stream(ss_ctx* ctx, void** stream_out) {
     return SS_OK;
 }
 
-int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats3) {
+int32_t ss_ctx_int8_stats(ss_ctx* ctx, int64_t* stats3) {  // 4 values, see the header
     SS_REQUIRE(ctx && stats3, "ss_ctx_int8_stats: null argument");
     for (int i = 0; i < 3; ++i) stats3[i] = ctx->int8_stats[i];
+    stats3[3] = ctx->int8_last_pairs;
     return SS_OK;
 }
 
@@ -686,6 +687,20 @@ static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, Chain
     w->kf = w->ks + round_up(ns, 64);
     w->kt = w->kf + round_up(nf, 64);
     SS_TRY(degrees_async(ctx, Xs, Y, w->ks, Xs ? w->kf : nullptr, w->kt));
+    if (Xs && precision == SS_PRECISION_F64_INT8) {
+        // INT8-sliced mode: fold the 1/ks of Wst = Y ./ ks into the rows of Xs, T = ((Xs ./ ks)' * Y) ./ kf
+        // (x/k * y instead of x * (y/k): one rounding apart).  Y itself is then an operand, and a 0/1 label matrix
+        // is a single 8-bit plane: 6 slice pairs instead of 21.
+        const int64_t ldx = round_up(ns, 16);
+        SS_TRY(scratch_get(ctx, 1, size_t(ldx) * size_t(nf) * 8, &p));
+        double* Xk = static_cast<double*>(p);
+        SS_TRY(launch_spread_rows(ctx, Xs->d, ns, nf, Xs->ld, w->ks, Xk, ldx));
+        w->ldt = round_up(nf, 16);
+        SS_TRY(scratch_get(ctx, 2, size_t(w->ldt) * size_t(nt) * 8, &p));
+        w->T = static_cast<double*>(p);
+        SS_TRY(chain_gemm(ctx, precision, SS_OP_T, Xk, ldx, Y->d, Y->ld, w->T, w->ldt, nf, nt, ns, w->kf, nullptr));
+        return SS_OK;
+    }
     w->ldw = round_up(ns, 16);
     SS_TRY(scratch_get(ctx, 1, size_t(w->ldw) * size_t(nt) * 8, &p));
     w->Wst = static_cast<double*>(p);

@@ -57,6 +57,7 @@ struct ss_ctx {
     // int8-sliced products since context creation: {products, products re-run on the DMMA path, entries that
     // failed the certificate in the last product}
     int64_t int8_stats[3] = {0, 0, 0};
+    int int8_last_pairs = 0;  // slice pairs of the last int8 product (planes of zeros are skipped)
     // workspaces reused across predict calls (never shrink)
     ss::Scratch ws[16];
     int32_t* tile_counter = nullptr;

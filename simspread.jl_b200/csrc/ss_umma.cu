@@ -71,9 +71,11 @@ struct UmmaParams {
     const double* rscale;  // integer mode: 2^ea[m]
     const double* cscale;  // integer mode: 2^eb[n]
     int* sync_prog;        // loose lockstep of the producers (see ss_gemm.cu), optional
-    // integer mode, a-posteriori certificate: an entry passes if acc >= cert * 2^ea[m] * 2^eb[n] (its absolute
-    // error bound is then <= tol * acc) or if it is exactly 0 and no operand entry was truncated to 0
-    double cert;
+    // integer mode, a-posteriori certificate: an entry passes if acc >= bound(m, n) / tol (see launch_gemm_i8) or if
+    // it is exactly 0 and no operand entry was truncated to 0
+    double certA, certB, certD;     // (truncation of A, truncation of B, dropped slice pairs * K) / tol
+    const double* rsum;             // sum_k |A[m,k]|
+    const double* csum;             // sum_k |B[k,n]|
     int zero_ok;
     unsigned long long* cert_fail;  // number of entries that did not pass (null: no check)
 };
@@ -254,7 +256,6 @@ __global__ void __launch_bounds__(U_THREADS, 1)
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
-              unsigned nfail = 0;
             for (int g = 0; g < p.ngroups; ++g, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -291,8 +292,9 @@ __global__ void __launch_bounds__(U_THREADS, 1)
             const UTile tc = utile(tile, p.tiles_m, p.tiles_n);
             const int m0 = tc.tm * UM, n0 = tc.tn * UN;
             const int row = m0 + 32 * ew + lane;
-            double inv = 1.0, rs = 1.0;
+            double inv = 1.0, rs = 1.0, rsm = 0.0;
             bool zero_row = false;
+            if (KIND == 1 && p.cert_fail && row < p.M) rsm = __ldg(p.rsum + row);
             if (row < p.M) {
                 if (p.row_div) {
                     const int d = __ldg(p.row_div + row);
@@ -330,7 +332,10 @@ __global__ void __launch_bounds__(U_THREADS, 1)
                                 }
                                 if (last) {
                                     if (KIND == 1 && p.cert_fail) {
-                                        const bool pass = (v >= p.cert * rs * __ldg(p.cscale + col)) || (v == 0.0 && p.zero_ok);
+                                        const double cs_ = __ldg(p.cscale + col);
+                                        const double need = p.certA * rs * __ldg(p.csum + col) + p.certB * cs_ * rsm + p.certD * rs * cs_;
+                                        // 1 % slack covers the FP64 rounding of the recombination (<= ngroups * 2^-53 relative)
+                                        const bool pass = (v * 0.99 >= need) || (v == 0.0 && p.zero_ok);
                                         nfail += pass ? 0u : 1u;
                                     }
                                     if (p.row_div) v = zero_row ? 0.0 : v / inv;
@@ -455,25 +460,33 @@ __device__ __forceinline__ double pow2_above(double mx) {
 // k-contiguous source: element (k, j) at src[j*ld + k]; one block per row j
 __global__ void __launch_bounds__(256)
     rowscale_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, double* __restrict__ scale,
-                           int* __restrict__ flags) {
-    __shared__ double smx[256];
+                           double* __restrict__ sums, int* __restrict__ flags) {
+    __shared__ double smx[256], ssm[256];
     for (int64_t j = blockIdx.x; j < J; j += gridDim.x) {
-        double mx = 0.0;
+        double mx = 0.0, sm = 0.0;
         int bad = 0;
         for (int64_t k = threadIdx.x; k < K; k += 256) {
             const double x = src[j * ld + k];
             if (x < 0.0) bad |= 1;
             if (!(fabs(x) <= 1.7976931348623157e308)) bad |= 2;
             mx = fmax(mx, fabs(x));
+            sm += fabs(x);
         }
         if (bad) atomicOr(flags, bad);
         smx[threadIdx.x] = mx;
+        ssm[threadIdx.x] = sm;
         __syncthreads();
         for (int st = 128; st > 0; st >>= 1) {
-            if (threadIdx.x < st) smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + st]);
+            if (threadIdx.x < st) {
+                smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + st]);
+                ssm[threadIdx.x] += ssm[threadIdx.x + st];
+            }
             __syncthreads();
         }
-        if (threadIdx.x == 0) scale[j] = pow2_above(smx[0]);
+        if (threadIdx.x == 0) {
+            scale[j] = pow2_above(smx[0]);
+            sums[j] = ssm[0] * (1.0 + 1e-12);  // an upper bound of the exact sum (rounding of the reduction)
+        }
         __syncthreads();
     }
 }
@@ -481,50 +494,68 @@ __global__ void __launch_bounds__(256)
 // m-contiguous source: element (m, k) at src[k*ld + m]; one thread per row m (coalesced over m)
 __global__ void __launch_bounds__(256)
     rowscale_mmajor_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, double* __restrict__ scale,
-                           int* __restrict__ flags) {
+                           double* __restrict__ sums, int* __restrict__ flags) {
     const int64_t m = int64_t(blockIdx.x) * 256 + threadIdx.x;
     if (m >= M) return;
-    double mx = 0.0;
+    double mx = 0.0, sm = 0.0;
     int bad = 0;
     for (int64_t k = 0; k < K; ++k) {
         const double x = __ldg(src + k * ld + m);
         if (x < 0.0) bad |= 1;
         if (!(fabs(x) <= 1.7976931348623157e308)) bad |= 2;
         mx = fmax(mx, fabs(x));
+        sm += fabs(x);
     }
     if (bad) atomicOr(flags, bad);
     scale[m] = pow2_above(mx);
+    sums[m] = sm * (1.0 + 1e-12);
 }
 
 // r in [0,1) -> S unsigned 8-bit digits, most significant first (all operations exact)
+// returns the mask of planes that received a non-zero digit
 template <int DUMMY = 0>
-__device__ __forceinline__ void slice_digits(double r, int S, uint8_t* out, int64_t plane, int* flags) {
+// bit 31 of the result: the entry is not exactly representable in S digits (it was truncated)
+__device__ __forceinline__ unsigned slice_digits(double r, int S, uint8_t* out, int64_t plane, int* flags) {
     if (r != 0.0 && r < ldexp(1.0, -8 * S)) atomicOr(flags, 4);  // a non-zero entry whose digits are all 0
+    unsigned used = 0;
     for (int i = 0; i < S; ++i) {
         r *= 256.0;
         const double q = floor(r);
         r -= q;
         out[int64_t(i) * plane] = uint8_t(int(q));
+        used |= (q != 0.0 ? 1u : 0u) << i;
     }
+    if (r != 0.0) used |= 0x80000000u;
+    return used;
+}
+
+// planes that hold only zeros need no tensor-core pass (a 0/1 label matrix is ONE plane): OR the per-thread masks
+__device__ __forceinline__ void publish_planes(unsigned used, int* plane_mask) {
+    used = __reduce_or_sync(0xffffffffu, used);
+    if ((threadIdx.x & 31) == 0 && used) atomicOr(plane_mask, int(used));
 }
 
 // k-contiguous source -> planes[i][j*kp + k]
 __global__ void __launch_bounds__(256)
     slice_kmajor_kernel(const double* __restrict__ src, int64_t K, int64_t J, int64_t ld, const double* __restrict__ scale,
-                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags) {
+                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags,
+                        int* __restrict__ plane_mask) {
     const int64_t k = int64_t(blockIdx.x) * 256 + threadIdx.x;
-    if (k >= kp) return;
     const int64_t plane = J * kp;
-    for (int64_t j = blockIdx.y; j < J; j += gridDim.y) {
-        const double x = (k < K) ? src[j * ld + k] : 0.0;
-        slice_digits(fabs(x) / scale[j], S, planes + j * kp + k, plane, flags);  // scale is a power of two: exact
-    }
+    unsigned used = 0;
+    if (k < kp)
+        for (int64_t j = blockIdx.y; j < J; j += gridDim.y) {
+            const double x = (k < K) ? src[j * ld + k] : 0.0;
+            used |= slice_digits(fabs(x) / scale[j], S, planes + j * kp + k, plane, flags);  // scale is a power of two: exact
+        }
+    publish_planes(used, plane_mask);
 }
 
 // m-contiguous source -> planes[i][m*kp + k] (32x32 transpose through shared memory)
 __global__ void __launch_bounds__(256)
     slice_mmajor_kernel(const double* __restrict__ src, int64_t M, int64_t K, int64_t ld, const double* __restrict__ scale,
-                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags) {
+                        int S, uint8_t* __restrict__ planes, int64_t kp, int* __restrict__ flags,
+                        int* __restrict__ plane_mask) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t m0 = int64_t(blockIdx.x) * 32, k0 = int64_t(blockIdx.y) * 32;
@@ -535,11 +566,13 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     const int64_t plane = M * kp;
+    unsigned used = 0;
 #pragma unroll
     for (int j = ty; j < 32; j += 8) {
         const int64_t m = m0 + j, k = k0 + tx;
-        if (m < M && k < kp) slice_digits(fabs(tile[tx][j]) / scale[m], S, planes + m * kp + k, plane, flags);
+        if (m < M && k < kp) used |= slice_digits(fabs(tile[tx][j]) / scale[m], S, planes + m * kp + k, plane, flags);
     }
+    publish_planes(used, plane_mask);
 }
 
 inline unsigned grid_y_for(const ss_ctx* ctx, int64_t gx, int64_t n) {
@@ -654,38 +687,43 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
     const int64_t per_group = int64_t(4294967295.0 / (double(kp) * 65025.0));
     SS_REQUIRE(per_group >= 1, "gemm_i8: K = %lld is too long for exact INT32 accumulation (max 66048)", (long long)K);
     void* p;
-    SS_TRY(scratch_get(ctx, 14, size_t(S) * M * kp + size_t(M) * 8 + 64, &p));
+    SS_TRY(scratch_get(ctx, 14, size_t(S) * M * kp + size_t(M) * 16 + 64, &p));
     uint8_t* Ap = static_cast<uint8_t*>(p);
     double* rs = reinterpret_cast<double*>(Ap + size_t(S) * M * kp);
-    SS_TRY(scratch_get(ctx, 15, size_t(S) * N * kp + size_t(N) * 8 + 64, &p));
+    double* rsum = rs + M;
+    SS_TRY(scratch_get(ctx, 15, size_t(S) * N * kp + size_t(N) * 16 + 64, &p));
     uint8_t* Bp = static_cast<uint8_t*>(p);
     double* cs = reinterpret_cast<double*>(Bp + size_t(S) * N * kp);
-    int* flags = reinterpret_cast<int*>(cs + N);
-    unsigned long long* cert_fail = reinterpret_cast<unsigned long long*>(flags + 2);
-    SS_CHECK_CUDA(cudaMemsetAsync(flags, 0, 16, ctx->stream));
+    double* csum = cs + N;
+    int* flags = reinterpret_cast<int*>(csum + N);
+    // flags[0]: bad-entry bits, flags[1] / flags[2]: planes of A / B that hold a non-zero digit
+    unsigned long long* cert_fail = reinterpret_cast<unsigned long long*>(flags + 4);
+    SS_CHECK_CUDA(cudaMemsetAsync(flags, 0, 24, ctx->stream));
     const int rgrid = ctx->sm_count * 8;
     if (opA == SS_OP_N) {
-        rowscale_mmajor_kernel<<<unsigned(ceil_div(M, 256)), 256, 0, ctx->stream>>>(A, M, K, lda, rs, flags);
+        rowscale_mmajor_kernel<<<unsigned(ceil_div(M, 256)), 256, 0, ctx->stream>>>(A, M, K, lda, rs, rsum, flags);
         dim3 g{unsigned(ceil_div(M, 32)), unsigned(ceil_div(kp, 32))};
         SS_REQUIRE(g.y <= 65535, "gemm_i8: K too large for the transpose grid");
-        slice_mmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, rs, S, Ap, kp, flags);
+        slice_mmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, M, K, lda, rs, S, Ap, kp, flags, flags + 1);
     } else {
-        rowscale_kmajor_kernel<<<unsigned(M < rgrid ? M : rgrid), 256, 0, ctx->stream>>>(A, K, M, lda, rs, flags);
+        rowscale_kmajor_kernel<<<unsigned(M < rgrid ? M : rgrid), 256, 0, ctx->stream>>>(A, K, M, lda, rs, rsum, flags);
         const int64_t gx = ceil_div(kp, 256);
         dim3 g{unsigned(gx), grid_y_for(ctx, gx, M)};
-        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, rs, S, Ap, kp, flags);
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(A, K, M, lda, rs, S, Ap, kp, flags, flags + 1);
     }
     {
-        rowscale_kmajor_kernel<<<unsigned(N < rgrid ? N : rgrid), 256, 0, ctx->stream>>>(B, K, N, ldb, cs, flags);
+        rowscale_kmajor_kernel<<<unsigned(N < rgrid ? N : rgrid), 256, 0, ctx->stream>>>(B, K, N, ldb, cs, csum, flags);
         const int64_t gx = ceil_div(kp, 256);
         dim3 g{unsigned(gx), grid_y_for(ctx, gx, N)};
-        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, cs, S, Bp, kp, flags);
+        slice_kmajor_kernel<<<g, 256, 0, ctx->stream>>>(B, K, N, ldb, cs, S, Bp, kp, flags, flags + 2);
     }
     ctx->launches += 4;
     SS_CHECK_CUDA(cudaGetLastError());
-    int hflags = 0;
-    SS_CHECK_CUDA(cudaMemcpyAsync(&hflags, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int hf[3] = {0, 0, 0};
+    SS_CHECK_CUDA(cudaMemcpyAsync(hf, flags, 12, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int hflags = hf[0];
+    const unsigned planesA = unsigned(hf[1]), planesB = unsigned(hf[2]);
     if (hflags & 3) {
         set_error("the int8-sliced precision mode needs finite, non-negative operands (%s entry found); "
                   "use the default FP64 mode", (hflags & 2) ? "NaN/Inf" : "negative");
@@ -707,6 +745,10 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
     // c_format S32 (2) | a_format / b_format unsigned 8-bit (0) | K-major | N>>3 | M>>4
     q.idesc = (2u << 4) | (uint32_t(UN >> 3) << 17) | (uint32_t(UM >> 4) << 24);
     // slice i (1-based weight 2^(-8i)) x slice j: keep i + j <= S + 1; smallest terms first
+    double dropped = 0.0;  // sum over the dropped pairs of non-zero planes of 2^(16 - 8(i+j)) >= q_i q_j 2^(-8(i+j))
+    for (int i = 1; i <= S; ++i)
+        for (int j = 1; j <= S; ++j)
+            if (i + j > S + 1 && ((planesA >> (i - 1)) & 1) && ((planesB >> (j - 1)) & 1)) dropped += ldexp(1.0, 16 - 8 * (i + j));
     int np = 0, ng = 0;
     q.gstart[0] = 0;
     for (int d = S + 1; d >= 2; --d) {
@@ -714,6 +756,8 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
         for (int i = 1; i <= S; ++i) {
             const int j = d - i;
             if (j < 1 || j > S) continue;
+            // a plane of zeros contributes nothing (keep the leading pair so that C is always written)
+            if ((!((planesA >> (i - 1)) & 1) || !((planesB >> (j - 1)) & 1)) && !(i == 1 && j == 1)) continue;
             if (in_group == per_group) {
                 q.gscale[ng] = ldexp(1.0, -8 * d);
                 q.gstart[++ng] = np;
@@ -729,7 +773,8 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
             q.gstart[++ng] = np;
         }
     }
-    SS_REQUIRE(np <= MAXPAIR && ng <= MAXGRP, "gemm_i8: too many slice pairs");
+    SS_REQUIRE(np >= 1 && np <= MAXPAIR && ng <= MAXGRP, "gemm_i8: bad number of slice pairs");
+    ctx->int8_last_pairs = np;
     q.ngroups = ng;
     q.C = C;
     q.ldc = ldc;
@@ -737,11 +782,18 @@ int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const
     q.col_flag = col_flag;
     q.rscale = rs;
     q.cscale = cs;
-    // A-posteriori certificate.  With x = 2^e sum_i q_i 2^(-8i) + d, 0 <= d < 2^(e-8S) (truncation) and the slice pairs
-    // with i + j > S + 1 dropped (each < 2^(16-8(i+j))), the absolute error of an entry is below
-    // K * (S + 1.5) * 2^(-8S) * 2^ea[m] * 2^eb[n]; it is <= tol * entry as soon as entry >= cert * 2^ea * 2^eb.
+    // A-posteriori certificate.  With x = 2^e (sum_i q_i 2^(-8i) + d), 0 <= d < 2^(-8S) only if x is not exactly
+    // representable (flag from the slicing), the absolute error of entry (m, n) is below
+    //   tA * 2^ea[m] * sum_k |B[k,n]|  +  tB * 2^eb[n] * sum_k |A[m,k]|  +  dropped * K * 2^ea[m] * 2^eb[n]
+    // (tA = 2^(-8S) if A was truncated, else 0; dropped = the slice pairs left out, zero planes not counted).
+    // An entry passes when this is <= tol * entry.  A 0/1 operand is exact and costs nothing here.
     const bool certify = uncertified != nullptr && cert_tol > 0.0;
-    q.cert = certify ? double(K) * (double(S) + 1.5) * ldexp(1.0, -8 * S) / cert_tol : 0.0;
+    const double trunc = ldexp(1.0, -8 * S) * 1.0000001;
+    q.certA = certify && (planesA >> 31) ? trunc / cert_tol : 0.0;
+    q.certB = certify && (planesB >> 31) ? trunc / cert_tol : 0.0;
+    q.certD = certify ? dropped * double(K) / cert_tol : 0.0;
+    q.rsum = rsum;
+    q.csum = csum;
     q.zero_ok = (hflags & 4) ? 0 : 1;
     q.cert_fail = certify ? cert_fail : nullptr;
     SS_TRY(launch_umma<1>(ctx, maps, q, 2.0 * double(M) * double(N) * double(K)));

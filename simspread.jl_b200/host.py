@@ -60,9 +60,15 @@ class Context:
     def int8_stats(self):
         """(products on the INT8 tensor pipe, products re-run in FP64 after a failed certificate, entries that failed
         in the last product) -- bookkeeping of precision="f64_int8"."""
-        out = (C.c_int64 * 3)()
+        out = (C.c_int64 * 4)()
         check(lib().ss_ctx_int8_stats(self.h, out))
         return int(out[0]), int(out[1]), int(out[2])
+
+    def int8_last_pairs(self) -> int:
+        """Slice pairs of the last int8 product (21 for two general operands with 6 slices, 6 when one is 0/1)."""
+        out = (C.c_int64 * 4)()
+        check(lib().ss_ctx_int8_stats(self.h, out))
+        return int(out[3])
 
     def profile(self, enable: bool):
         check(lib().ss_ctx_profile(self.h, int(enable)))

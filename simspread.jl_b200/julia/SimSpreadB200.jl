@@ -16,7 +16,7 @@ using Random
 
 export cutoff, cutoff!, featurize, featurize!, k, construct, spread, predict, clean!,
     AuROC, AuPRC, BEDROC, recallatL, precisionatL, validity_ratio,
-    maxperformance, meanperformance, meanstdperformance, jaccard_featurize
+    maxperformance, meanperformance, meanstdperformance, jaccard_featurize, recommend_topl, read_namedmatrix
 
 const libss = get(ENV, "SIMSPREAD_B200_LIB",
     joinpath(@__DIR__, "..", "lib", "libsimspread_b200.so"))
@@ -399,5 +399,62 @@ end
 maxperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = _sweep(y, yhat, metric)[1]
 meanperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = _sweep(y, yhat, metric)[2]
 meanstdperformance(y::AbstractVector, yhat::AbstractVector, metric::Function) = (o = _sweep(y, yhat, metric); (o[2], o[3]))
+
+# ---------------------------------------------------------------------------------------------
+# sparse 2-layer NBI with fused top-L (BASELINE config 5): `predict(construct(y, X), y)` of the reference on a
+# graph without feature layer (src/core.jl:446-466), reduced to `sortperm(rev=true)[1:L]` per source
+# (src/performance.jl:315) without materialising the score matrix.  Returns (idx, val): L x sources, 1-based
+# target indices (0 = padding) and scores.  `srange` restricts the sources (sharding over GPUs).
+# ---------------------------------------------------------------------------------------------
+function recommend_topl(y::AbstractMatrix; L::Integer=20, srange::UnitRange{Int}=1:size(y, 1))
+    ns, nt = size(y)
+    weighted = any(v -> v != 0 && v != 1, y)
+    d = DMat(Matrix{Float64}(y))
+    α = weighted ? -Inf : 5e-324          # keep every (positive) entry
+    hy, hyt = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ss_featurize_csr, libss), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Cint, Ptr{Ptr{Cvoid}}),
+        ctx().h, d.h, α, Cint(weighted), hy))
+    check(ccall((:ss_featurize_csc, libss), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Cint, Ptr{Ptr{Cvoid}}),
+        ctx().h, d.h, α, Cint(weighted), hyt))
+    idx, val = DIVec(L * ns), DMat(L, ns)
+    try
+        check(ccall((:ss_recommend_topl, libss), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+            ctx().h, hy[], hyt[], Cint(L), first(srange) - 1, last(srange), idx.h, val.h))
+    finally
+        ccall((:ss_csr_destroy, libss), Cint, (Ptr{Cvoid},), hy[])
+        ccall((:ss_csr_destroy, libss), Cint, (Ptr{Cvoid},), hyt[])
+    end
+    return reshape(Vector(idx), L, ns) .+ Int32(1), Matrix(val)
+end
+
+# ---------------------------------------------------------------------------------------------
+# utils.jl: read_namedmatrix with the value block parsed by all host cores (ss_text_matrix_read); names, the
+# "R#i" / "C#j" defaults and the sort by name are the reference's (src/utils.jl:24-53).
+# ---------------------------------------------------------------------------------------------
+function read_namedmatrix(filepath::String, delimiter::Char=' ', valuetype::Type=Float64; rows::Bool=true, cols::Bool=true)
+    nl, nf = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:ss_text_matrix_dims, libss), Cint, (Cstring, Cint, Ptr{Int64}, Ptr{Int64}),
+        filepath, Cint(delimiter), nl, nf))
+    nr, nc = nl[] - Int(cols), nf[] - Int(rows)
+    vals = Matrix{Float64}(undef, nr, nc)
+    GC.@preserve vals check(ccall((:ss_text_matrix_read, libss), Cint,
+        (Cstring, Cint, Cint, Cint, Ptr{Float64}, Int64, Int64, Int64),
+        filepath, Cint(delimiter), Cint(cols), Cint(rows), vals, nr, nc, max(nr, 1)))
+    row_names = ["R#$i" for i in 1:nr]
+    col_names = ["C#$j" for j in 1:nc]
+    if rows || cols
+        for (i, line) in enumerate(eachline(filepath))
+            if i == 1 && cols
+                col_names = String.(split(line, delimiter))[(rows ? 2 : 1):end]
+            elseif rows && i - Int(cols) <= nr
+                row_names[i - Int(cols)] = String(first(split(line, delimiter; limit=2)))
+            end
+            !rows && break
+        end
+    end
+    M = NamedArray(valuetype === Float64 ? vals : valuetype.(vals), (row_names, col_names))
+    return M[sort(row_names), sort(col_names)]
+end
 
 end # module

@@ -688,7 +688,8 @@ def test_bedroc_and_threshold_sweeps_against_oracle(ss, o):
     assert math.isnan(ss.maxperformance(yn, rng.random(50), ss.recall))
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (129, 257, 133), (300, 520, 2600), (64, 200, 20000)])
+# (1700, 3100, 300): 14 x 13 = 182 tiles > 148 SMs -- the persistent tile loop and the producers' lockstep
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (129, 257, 133), (300, 520, 2600), (64, 200, 20000), (1700, 3100, 300)])
 @pytest.mark.parametrize("op", ["N", "T"])
 def test_gemm_f64_from_int8_slices(ss, M, N, K, op):
     """Opt-in FP64-grade mode on the INT8 tensor pipe: exact integer slice products, FP64
@@ -751,9 +752,13 @@ def test_int8_mode_certificate_and_fp64_fallback(ss):
         assert np.max(np.abs(got[nz] - want[nz]) / want[nz]) < RTOL
         return after[1] - before[1], after[2]
 
-    # (1) dense similarity-like operands: certified, no fallback
+    # (1) dense similarity-like operands: certified, no fallback; 6 x 6 slices with i + j <= 7 -> 21 pairs
     A, B = rng.random((M, K)), rng.random((K, N))
-    assert run(A, B) == (0, 0)
+    assert run(A, B) == (0, 0) and ctx.int8_last_pairs() == 21
+    # (1b) a 0/1 operand is a single 8-bit plane: planes of zeros are skipped -> 6 pairs, same certified result
+    Bbin = (rng.random((K, N)) < 0.05).astype(float)
+    assert run(A, Bbin) == (0, 0) and ctx.int8_last_pairs() == 6
+    assert run((A > 0.5).astype(float), Bbin) == (0, 0) and ctx.int8_last_pairs() == 1
     # (2) block structure: exact zeros (disjoint supports) are certified as zeros
     A2, B2 = A.copy(), B.copy()
     A2[:, K // 2:] = 0.0
