@@ -1,9 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 420 python -X faulthandler -c "
-import faulthandler, sys, runpy
-faulthandler.dump_traceback_later(150, repeat=True)
-sys.argv = ['bench.py', '--steps', '1', '--warmup', '1']
-runpy.run_path('bench.py', run_name='__main__')
-" > gpurun_out/bench_diag.log 2> gpurun_out/bench_diag.err; echo "bench exit $?"
-tail -c 1500 gpurun_out/bench_diag.log; echo; grep -n "File\|line\|Thread" gpurun_out/bench_diag.err | head -40
+timeout 400 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "int8" > gpurun_out/pytest_int8.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_int8.log
+timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_default.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['achieved'], d['roofline']['frac'], d['e2e']['value'], d['check'], d['opt_in_f64_int8'], d['cpu_baseline']['value'], d['gpu_launches'], d['clocks'])"
