@@ -476,31 +476,8 @@ def run_b200(args):
                       sharded,
                       (mXq, mXs, mY, mR, bR, ldr))
 
-    # ---- opt-in FP64-grade mode on the INT8 tensor pipe, measured beside the headline (untimed for `value`)
-    int8 = None
-    if world == 1 and not pflag and not args.no_check:
-        flag8 = SS_PREDICT_CLEAN | (3 << 4)
-        ref_sample = bR[tt, tq].clone()  # FP64 DMMA result at the sampled entries
-        check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, flag8, None))  # warm-up (allocates slices)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(ext)
-        check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, flag8, None))
-        f1.record(ext)
-        barrier()
-        ms8 = f0.elapsed_time(f1)
-        st8 = ctx.int8_stats()
-        got8 = bR[tt, tq]
-        rel8 = ((got8 - want).abs() / want.abs().clamp_min(1e-300)).max().item()
-        int8 = {"mode": "precision=f64_int8: 6 unsigned 8-bit slices per operand, 21 exact INT32 slice products on "
-                        "tcgen05 kind::i8, FP64 recombination; every entry certified a posteriori (error bound <= 4e-13 "
-                        "of the entry per product), a product that fails is re-run on the FP64 DMMA path (opt-in)",
-                "products_on_int8_pipe": st8[0], "products_rerun_in_fp64": st8[1], "uncertified_entries_last_product": st8[2],
-                "value": nq * nt / (ms8 * 1e-3), "unit": UNIT, "ms_per_step": ms8,
-                "speedup_vs_fp64_dmma": ms_step / ms8, "max_rel_err_sampled": rel8,
-                "max_rel_diff_vs_dmma_sampled": ((got8 - ref_sample).abs() / ref_sample.abs().clamp_min(1e-300)).max().item()}
-        check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, SS_PREDICT_CLEAN, None))  # restore the FP64 result
-
+    # ---- the line (everything the contract asks for is known at this point) --------------------------------
+    line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -518,8 +495,52 @@ def run_b200(args):
                          if sharded.b.mirrors is not None else "NCCL all-gather")),
                        "l2": "inputs (27 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "check": checkres, "opt_in_f64_int8": int8,
+            "cpu_baseline": cpu, "check": checkres, "opt_in_f64_int8": None,
         }
+
+    # ---- opt-in FP64-grade mode on the INT8 tensor pipe, measured beside the headline (untimed for `value`).
+    # A watchdog prints the line without it if this side measurement does not finish: an opt-in mode must never
+    # cost the headline (the watchdog thread runs while the main thread sits in the library call).
+    if world == 1 and not pflag and not args.no_check:
+        import threading
+
+        def _bail():
+            line["opt_in_f64_int8"] = {"error": "the opt-in INT8 measurement did not finish within 240 s; not reported"}
+            print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(240.0, _bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            flag8 = SS_PREDICT_CLEAN | (3 << 4)
+            ref_sample = bR[tt, tq].clone()  # FP64 DMMA result at the sampled entries
+            check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, flag8, None))  # warm-up (allocates slices)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(ext)
+            check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, flag8, None))
+            f1.record(ext)
+            barrier()
+            ms8 = f0.elapsed_time(f1)
+            st8 = ctx.int8_stats()
+            got8 = bR[tt, tq]
+            rel8 = ((got8 - want).abs() / want.abs().clamp_min(1e-300)).max().item()
+            line["opt_in_f64_int8"] = {
+                "mode": "precision=f64_int8: 6 unsigned 8-bit slices per operand, exact INT32 slice products on tcgen05 "
+                        "kind::i8 (planes of zeros skipped: 6 pairs for the 0/1 label matrix, 21 for R = Xq*T), FP64 "
+                        "recombination; every entry certified a posteriori (error bound <= 4e-13 of the entry per "
+                        "product), a product that fails is re-run on the FP64 DMMA path (opt-in)",
+                "products_on_int8_pipe": st8[0], "products_rerun_in_fp64": st8[1], "uncertified_entries_last_product": st8[2],
+                "value": nq * nt / (ms8 * 1e-3), "unit": UNIT, "ms_per_step": ms8,
+                "speedup_vs_fp64_dmma": ms_step / ms8, "max_rel_err_sampled": rel8,
+                "max_rel_diff_vs_dmma_sampled": ((got8 - ref_sample).abs() / ref_sample.abs().clamp_min(1e-300)).max().item()}
+            check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, SS_PREDICT_CLEAN, None))  # restore the FP64 result
+        except Exception as exc:  # noqa: BLE001 -- the side measurement may fail, the headline may not
+            line["opt_in_f64_int8"] = {"error": f"{type(exc).__name__}: {exc}"}
+        dog.cancel()
+
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
