@@ -233,3 +233,24 @@ def test_tanimoto_bits_matches_jaccard_of_indicator_vectors():
     bb = np.unpackbits(FB.view(np.uint8), axis=1).astype(float)
     J = o.jaccard_similarity(ba, bb)
     assert np.allclose(T, J, rtol=0, atol=2.3e-16) and T[2, 1] == 1.0  # J goes through 1 - (1 - q)
+
+
+def test_auroc_auprc_restatement_against_scikit_learn_counts():
+    """AuROC / AuPRC have no golden in the reference (placeholders at test/runtests.jl:210-217), so the restatement of
+    MLBase.roc + Trapz.trapz is cross-checked against an independent implementation of the confusion counts:
+    scikit-learn's roc_curve / precision_recall_curve give (fpr, tpr) / (precision, recall) at every unique threshold;
+    the reference's curve is exactly those points WITHOUT sklearn's synthetic anchors ((0,0) for ROC, (recall 0,
+    precision 1) for PR) -- src/performance.jl:53-61, 78-86, SURVEY App. A.16."""
+    sk = pytest.importorskip("sklearn.metrics")
+    trapezoid = getattr(np, "trapezoid", None) or np.trapz
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        n = 1500 + 100 * trial
+        s = np.round(rng.random(n), 2 if trial % 2 else 6)  # heavy ties / almost none
+        y = rng.random(n) < 0.1 + 0.5 * s
+        fpr, tpr, _ = sk.roc_curve(y, s, drop_intermediate=False)
+        assert o.AuROC(y, s) == pytest.approx(abs(trapezoid(tpr[1:], fpr[1:])), rel=1e-12)
+        prec, rec, _ = sk.precision_recall_curve(y, s)
+        assert o.AuPRC(y, s) == pytest.approx(abs(trapezoid(prec[:-1], rec[:-1])), rel=1e-12)
+    # the documented consequence of the missing anchors (SURVEY App. A.16): 2/3 instead of the textbook 0.75
+    assert o.AuROC(np.array([1, 0, 1, 0, 0], bool), np.array([.9, .9, .7, .1, .1])) == pytest.approx(2 / 3, rel=1e-12)

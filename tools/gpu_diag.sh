@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "int8" > gpurun_out/pytest_int8.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_int8.log
 timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_default.log | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['achieved'], d['roofline']['frac'], d['e2e']['value'], d['check'], d['opt_in_f64_int8'], d['cpu_baseline']['value'], d['gpu_launches'], d['clocks'])"
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['check']['ok'], d['opt_in_f64_int8']['value'], d['opt_in_f64_int8']['products_rerun_in_fp64'], d['cpu_baseline']['value'], d['gpu_launches'])"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_v2.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches_v2.log 2>&1; echo "ncu exit $?"
