@@ -162,3 +162,82 @@ def test_writedlm_layout_and_julia_number_format(built, tmp_path):
     assert np.array_equal(back.array, X.array) and back.names(1) == X.names(1) and back.names(2) == X.names(2)
     for v, s_ in [(100000.0, "100000.0"), (1e6, "1.0e6"), (0.0001, "0.0001"), (0.1 + 0.2, "0.30000000000000004"), (5e-324, "5.0e-324")]:
         assert _jl_string(v) == s_
+
+
+# ---------------------------------------------------------------------------------------------
+# the Julia host layer cannot be executed here (no Julia in the image): static checks of its ccalls
+# ---------------------------------------------------------------------------------------------
+
+
+def _split_top_level(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_ccalls_match_the_header():
+    """Every `ccall((:ss_x, libss), Cint, (argtypes...), args...)` of SimSpreadB200.jl must name a function the header
+    declares, with as many argument types (and arguments) as the C prototype has parameters, and with Julia types whose
+    width matches the C parameter (pointers <-> Ptr/Cstring/Ref, int32 <-> Cint/Cuint, int64 <-> Int64, double <-> Float64)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "simspread.jl_b200", "julia", "SimSpreadB200.jl")).read()
+    hdr = open(os.path.join(root, "include", "simspread_b200.h")).read()
+    protos = {}
+    for m in re.finditer(r"SS_API\s+[\w\s\*]+?\b(ss_[a-z0-9_]+)\(([^;]*?)\);", hdr, flags=re.S):
+        params = [p.strip() for p in _split_top_level(m.group(2).replace("\n", " "))]
+        protos[m.group(1)] = [] if params == ["void"] else params
+
+    def c_class(p):
+        if "*" in p:
+            return "ptr"
+        if re.search(r"\bdouble\b", p):
+            return "f64"
+        if re.search(r"\b(int64_t|uint64_t)\b", p):
+            return "i64"
+        if re.search(r"\b(int32_t|uint32_t|int)\b", p):
+            return "i32"
+        raise AssertionError(p)
+
+    def jl_class(t):
+        t = t.strip()
+        if t.startswith("Ptr{") or t.startswith("Ref{") or t in ("Cstring",):
+            return "ptr"
+        return {"Float64": "f64", "Int64": "i64", "Cint": "i32", "Cuint": "i32", "Int32": "i32", "UInt32": "i32"}[t]
+
+    calls = 0
+    for m in re.finditer(r"ccall\(\(:(ss_[a-z0-9_]+),\s*libss\)", jl):
+        name = m.group(1)
+        assert name in protos, f"{name} is not declared in the header"
+        # the full ccall expression: balance parentheses from the opening one
+        i = m.start() + len("ccall")
+        depth, j = 0, i
+        while True:
+            depth += jl[j] == "("
+            depth -= jl[j] == ")"
+            j += 1
+            if depth == 0:
+                break
+        parts = _split_top_level(jl[i + 1:j - 1])
+        # parts: (:name, libss) | return type | (argtypes) | args...
+        assert parts[1] in ("Cint", "Cstring"), (name, parts[1])
+        argtypes = _split_top_level(parts[2].strip()[1:-1]) if parts[2].strip() not in ("()",) else []
+        args = parts[3:]
+        want = protos[name]
+        assert len(argtypes) == len(want), f"{name}: {len(argtypes)} Julia argument types, {len(want)} C parameters"
+        assert len(args) == len(want), f"{name}: {len(args)} arguments passed, {len(want)} C parameters"
+        for t, p in zip(argtypes, want):
+            assert jl_class(t) == c_class(p), f"{name}: Julia type {t} against C parameter `{p}`"
+        calls += 1
+    assert calls >= 30
