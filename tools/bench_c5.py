@@ -40,21 +40,25 @@ nnz = keys.numel()
 y_ptr = torch.zeros(ns + 1, dtype=torch.int32, device=dev)
 y_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=ns), 0).to(torch.int32)
 y_idx = cols.to(torch.int32)
-keyt = torch.sort(cols * ns + rows).values
+keyt, perm = torch.sort(cols * ns + rows)
 yt_ptr = torch.zeros(nt + 1, dtype=torch.int32, device=dev)
 yt_ptr[1:] = torch.cumsum(torch.bincount(keyt // ns, minlength=nt), 0).to(torch.int32)
 yt_idx = (keyt % ns).to(torch.int32)
-del keys, keyt, rows, cols
+WEIGHTED = os.environ.get("C5_WEIGHTED") == "1"  # ratings in [0.5, 1.5) instead of 0/1 edges
+y_val = (torch.rand(nnz, dtype=torch.float64, device=dev, generator=g) + 0.5) if WEIGHTED else None
+yt_val = y_val[perm].contiguous() if WEIGHTED else None
+del keys, keyt, rows, cols, perm
 torch.cuda.synchronize()
 
 
-def wrap(r, c, n, ptr, idx):
+def wrap(r, c, n, ptr, idx, val):
     h = C.c_void_p()
-    check(lib.ss_csr_wrap(ctx.h, r, c, n, C.c_void_p(ptr.data_ptr()), C.c_void_p(idx.data_ptr()), None, C.byref(h)))
+    check(lib.ss_csr_wrap(ctx.h, r, c, n, C.c_void_p(ptr.data_ptr()), C.c_void_p(idx.data_ptr()),
+                          C.c_void_p(val.data_ptr()) if val is not None else None, C.byref(h)))
     return h
 
 
-hY, hYT = wrap(ns, nt, nnz, y_ptr, y_idx), wrap(nt, ns, nnz, yt_ptr, yt_idx)
+hY, hYT = wrap(ns, nt, nnz, y_ptr, y_idx, y_val), wrap(nt, ns, nnz, yt_ptr, yt_idx, yt_val)
 idx = torch.full((ns, L), -2, dtype=torch.int32, device=dev)
 val = torch.zeros((ns, L), dtype=torch.float64, device=dev)
 vi, vm = C.c_void_p(), C.c_void_p()
@@ -82,12 +86,13 @@ kt = (yt_ptr[1:] - yt_ptr[:-1]).to(torch.float64)
 per_item = torch.zeros(nt, dtype=torch.float64, device=dev).index_add_(0, y_idx.long(), ks.repeat_interleave((y_ptr[1:] - y_ptr[:-1]).long()))
 pp = float(per_item[y_idx[: int(y_ptr[s_end])].long()].sum().item())
 # spot check: three users recomputed with torch sparse mat-vecs
-Ysp = torch.sparse_csr_tensor(y_ptr.long(), y_idx.long(), torch.ones(nnz, dtype=torch.float64, device=dev), size=(ns, nt))
-YTsp = torch.sparse_csr_tensor(yt_ptr.long(), yt_idx.long(), torch.ones(nnz, dtype=torch.float64, device=dev), size=(nt, ns))
+ones = torch.ones(nnz, dtype=torch.float64, device=dev)
+Ysp = torch.sparse_csr_tensor(y_ptr.long(), y_idx.long(), y_val if WEIGHTED else ones, size=(ns, nt))
+YTsp = torch.sparse_csr_tensor(yt_ptr.long(), yt_idx.long(), yt_val if WEIGHTED else ones, size=(nt, ns))
 worst = 0.0
 for s in (0, s_end // 2, s_end - 1):
     a = torch.zeros(nt, dtype=torch.float64, device=dev)
-    a[y_idx[y_ptr[s]:y_ptr[s + 1]].long()] = 1.0
+    a[y_idx[y_ptr[s]:y_ptr[s + 1]].long()] = y_val[y_ptr[s]:y_ptr[s + 1]] if WEIGHTED else 1.0
     v1 = torch.where(kt > 0, a / kt, torch.zeros_like(a))
     v2 = torch.mv(Ysp, v1)
     F = torch.mv(YTsp, torch.where(ks > 0, v2 / ks, torch.zeros_like(v2)))
@@ -95,7 +100,7 @@ for s in (0, s_end // 2, s_end - 1):
     got = val[s]
     worst = max(worst, float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item()))
     assert bool((F[idx[s].long()] - got).abs().max() <= 1e-12 * got.abs().max().clamp_min(1e-300))
-out = {"users": ns, "items": nt, "edges": nnz, "L": L, "degrees": os.environ.get("C5_DEGREES", "poisson"),
+out = {"users": ns, "items": nt, "edges": nnz, "L": L, "degrees": os.environ.get("C5_DEGREES", "poisson"), "weighted": WEIGHTED,
        "max_user_degree": int((y_ptr[1:] - y_ptr[:-1]).max().item()), "max_item_degree": int((yt_ptr[1:] - yt_ptr[:-1]).max().item()), "users_processed": s_end, "ms": ms, "wall_s": wall,
        "scores_per_s": s_end * nt / (ms * 1e-3), "partial_products": pp,
        "partial_products_per_s": pp / (ms * 1e-3), "achieved_gbs_4B_per_pp": pp * 4 / (ms * 1e-3) / 1e9,

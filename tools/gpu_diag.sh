@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_default.log | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['check']['ok'], d['opt_in_f64_int8']['value'], d['opt_in_f64_int8']['products_rerun_in_fp64'], d['cpu_baseline']['value'], d['gpu_launches'])"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_v2.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches_v2.log 2>&1; echo "ncu exit $?"
+C5_WEIGHTED=1 C5_REPS=3 SS_RECSYS_VERBOSE=1 timeout 400 python tools/bench_c5.py 2000000 500000 0.05 > gpurun_out/c5_weighted.log 2>&1; echo "weighted exit $?"; tail -1 gpurun_out/c5_weighted.log | cut -c1-800
+cp gpurun_out/c5.json gpurun_out/c5_weighted.json
