@@ -210,6 +210,16 @@ SS_API int32_t ss_ipc_close(ss_ctx* ctx, void* devptr);
  * context stream.  kt_out (optional) receives the target degrees used by clean!. */
 SS_API int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
                          uint32_t flags, ss_ivec* kt_out);
+/* k-fold cross-validation in one call (the user-side loop of docs/src/api.md:17-21 over construct / predict /
+ * clean!).  X: featurized N x N similarity matrix, Y: N' x Nt labels (both resident).  For fold f the
+ * queries are rows q_idx[q_ptr[f] .. q_ptr[f+1]) of X, the sources rows s_idx[s_ptr[f] ..) of X with their label rows
+ * ys_idx[s_ptr[f] ..) of Y, the features columns f_idx[f_ptr[f] ..) of X (host int32 arrays, 0-based: exactly the
+ * name filtering of src/core.jl:152-154 done by the host layer).  Rows [q_ptr[f] - q_ptr[0], ...) of R receive the
+ * predictions of fold f.  All folds are queued on the stream, one synchronisation at the end. */
+SS_API int32_t ss_predict_query_folds(ss_ctx* ctx, const ss_mat* X, const ss_mat* Y, int32_t nfolds, const int32_t* q_ptr,
+                                      const int32_t* q_idx, const int32_t* s_ptr, const int32_t* s_idx,
+                                      const int32_t* ys_idx, const int32_t* f_ptr, const int32_t* f_idx, ss_mat* R,
+                                      uint32_t flags);
 /* Sparse form of ss_predict_query for high-alpha (few-percent dense) feature blocks: Xq is the CSR
  * of the Nq x Nf query block, XsT the CSR of Xs' (Nf x Ns, from ss_featurize_csc), Y the dense
  * Ns x Nt label block.  Both products run as row-split SpMMs; R is dense column-major as before. */

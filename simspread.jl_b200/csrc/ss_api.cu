@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "ss_common.cuh"
 
 namespace ss {
@@ -737,6 +739,83 @@ int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const 
                       nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr));
     if (kt_out)
         SS_CHECK_CUDA(cudaMemcpyAsync(kt_out->d, w.kt, size_t(Y->cols) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// k-fold cross-validation in one call (the loop of docs/src/api.md:17-21): per fold the blocks
+// X[queries, features], X[sources, features], y[sources, targets] are extracted by index list (construct,
+// src/core.jl:167,171-172) and predict + clean! runs on them; everything is queued on the context stream with the
+// workspaces re-used fold after fold and ONE synchronisation at the end (a fold of an Enzyme-sized data set is tens of
+// microseconds of kernels: the per-fold host round trips were the cost).
+int32_t ss_predict_query_folds(ss_ctx* ctx, const ss_mat* X, const ss_mat* Y, int32_t nfolds, const int32_t* q_ptr,
+                               const int32_t* q_idx, const int32_t* s_ptr, const int32_t* s_idx, const int32_t* ys_idx,
+                               const int32_t* f_ptr, const int32_t* f_idx, ss_mat* R, uint32_t flags) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(X && Y && R && nfolds >= 0, "ss_predict_query_folds: bad argument");
+    if (nfolds == 0) return SS_OK;
+    SS_REQUIRE(q_ptr && q_idx && s_ptr && s_idx && ys_idx && f_ptr && f_idx, "ss_predict_query_folds: null index list");
+    const int64_t nt = Y->cols;
+    SS_REQUIRE(R->cols == nt && R->rows == q_ptr[nfolds] - q_ptr[0], "ss_predict_query_folds: R must be (all queries) x targets");
+    const uint32_t prec = flags & SS_PRECISION_MASK;
+    int64_t mq = 0, ms = 0, mf = 0;
+    for (int f = 0; f < nfolds; ++f) {
+        SS_REQUIRE(q_ptr[f + 1] >= q_ptr[f] && s_ptr[f + 1] >= s_ptr[f] && f_ptr[f + 1] >= f_ptr[f],
+                   "ss_predict_query_folds: index pointers must be non-decreasing");
+        mq = std::max<int64_t>(mq, q_ptr[f + 1] - q_ptr[f]);
+        ms = std::max<int64_t>(ms, s_ptr[f + 1] - s_ptr[f]);
+        mf = std::max<int64_t>(mf, f_ptr[f + 1] - f_ptr[f]);
+    }
+    for (int64_t i = q_ptr[0]; i < q_ptr[nfolds]; ++i) SS_REQUIRE(q_idx[i] >= 0 && q_idx[i] < X->rows, "ss_predict_query_folds: query index out of range");
+    for (int64_t i = s_ptr[0]; i < s_ptr[nfolds]; ++i)
+        SS_REQUIRE(s_idx[i] >= 0 && s_idx[i] < X->rows && ys_idx[i] >= 0 && ys_idx[i] < Y->rows, "ss_predict_query_folds: source index out of range");
+    for (int64_t i = f_ptr[0]; i < f_ptr[nfolds]; ++i) SS_REQUIRE(f_idx[i] >= 0 && f_idx[i] < X->cols, "ss_predict_query_folds: feature index out of range");
+    // index lists -> device, one copy
+    const int64_t nqi = q_ptr[nfolds] - q_ptr[0], nsi = s_ptr[nfolds] - s_ptr[0], nfi = f_ptr[nfolds] - f_ptr[0];
+    void* p;
+    SS_TRY(scratch_get(ctx, 16, size_t(nqi + 2 * nsi + nfi + 4) * 4, &p));
+    int32_t* dq = static_cast<int32_t*>(p);
+    int32_t* dsx = dq + nqi;
+    int32_t* dsy = dsx + nsi;
+    int32_t* df = dsy + nsi;
+    SS_CHECK_CUDA(cudaMemcpyAsync(dq, q_idx + q_ptr[0], size_t(nqi) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaMemcpyAsync(dsx, s_idx + s_ptr[0], size_t(nsi) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaMemcpyAsync(dsy, ys_idx + s_ptr[0], size_t(nsi) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SS_CHECK_CUDA(cudaMemcpyAsync(df, f_idx + f_ptr[0], size_t(nfi) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // block buffers sized for the largest fold
+    ss_mat bXq, bXs, bY, bR;
+    bXq.ctx = bXs.ctx = bY.ctx = bR.ctx = ctx;
+    SS_TRY(scratch_get(ctx, 17, size_t(round_up(std::max<int64_t>(mq, 1), 16)) * size_t(std::max<int64_t>(mf, 1)) * 8, &p));
+    bXq.d = static_cast<double*>(p);
+    SS_TRY(scratch_get(ctx, 18, size_t(round_up(std::max<int64_t>(ms, 1), 16)) * size_t(std::max<int64_t>(mf, 1)) * 8, &p));
+    bXs.d = static_cast<double*>(p);
+    SS_TRY(scratch_get(ctx, 19, size_t(round_up(std::max<int64_t>(ms, 1), 16)) * size_t(std::max<int64_t>(nt, 1)) * 8, &p));
+    bY.d = static_cast<double*>(p);
+    for (int f = 0; f < nfolds; ++f) {
+        const int64_t nq = q_ptr[f + 1] - q_ptr[f], ns = s_ptr[f + 1] - s_ptr[f], nf = f_ptr[f + 1] - f_ptr[f];
+        if (nq == 0 || nt == 0) continue;
+        const int64_t off = q_ptr[f] - q_ptr[0];
+        bR.d = R->d + off;  // rows [off, off + nq) of R
+        bR.rows = nq; bR.cols = nt; bR.ld = R->ld;
+        if (ns == 0 || nf == 0) {  // no sources / no features: every product is empty -> zeros
+            SS_CHECK_CUDA(cudaMemset2DAsync(bR.d, size_t(bR.ld) * 8, 0, size_t(nq) * 8, size_t(nt), ctx->stream));
+            continue;
+        }
+        bXq.rows = nq; bXq.cols = nf; bXq.ld = round_up(nq, 16);
+        bXs.rows = ns; bXs.cols = nf; bXs.ld = round_up(ns, 16);
+        bY.rows = ns; bY.cols = nt; bY.ld = round_up(ns, 16);
+        const int32_t* fq = dq + off;
+        const int32_t* fs = dsx + (s_ptr[f] - s_ptr[0]);
+        const int32_t* fy = dsy + (s_ptr[f] - s_ptr[0]);
+        const int32_t* ff = df + (f_ptr[f] - f_ptr[0]);
+        SS_TRY(launch_gather(ctx, X->d, X->ld, fq, ff, bXq.d, nq, nf, bXq.ld));
+        SS_TRY(launch_gather(ctx, X->d, X->ld, fs, ff, bXs.d, ns, nf, bXs.ld));
+        SS_TRY(launch_gather(ctx, Y->d, Y->ld, fy, nullptr, bY.d, ns, nt, bY.ld));
+        ChainWs w;
+        SS_TRY(chain_front(ctx, &bXs, &bY, &w, prec));
+        SS_TRY(chain_gemm(ctx, prec, SS_OP_N, bXq.d, bXq.ld, w.T, w.ldt, bR.d, bR.ld, nq, nt, nf, nullptr,
+                          (flags & SS_PREDICT_CLEAN) ? w.kt : nullptr));
+    }
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
 }

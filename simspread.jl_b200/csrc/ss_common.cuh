@@ -59,7 +59,7 @@ struct ss_ctx {
     int64_t int8_stats[3] = {0, 0, 0};
     int int8_last_pairs = 0;  // slice pairs of the last int8 product (planes of zeros are skipped)
     // workspaces reused across predict calls (never shrink)
-    ss::Scratch ws[16];
+    ss::Scratch ws[24];
     int32_t* tile_counter = nullptr;
     bool gemm_attr_set = false;
     // optional per-GEMM timing (ss_ctx_profile)

@@ -47,10 +47,22 @@ class NamedArray:
     def copy(self) -> "NamedArray":
         return NamedArray(self.array.copy(), self.names())
 
-    def index_of(self, wanted: Sequence[str], d: int) -> np.ndarray:
+    def _positions(self, d: int) -> dict:
+        """name -> first position along dimension d; cached against the identity of the name list (setnames and
+        every constructor install a fresh list, so a stale cache cannot be hit)."""
+        names = self._names[d - 1]
+        cache = self.__dict__.setdefault("_pos_cache", {})
+        hit = cache.get(d)
+        if hit is not None and hit[0] is names and hit[1] == len(names):
+            return hit[2]
         pos = {}
-        for i, n in enumerate(self._names[d - 1]):
+        for i, n in enumerate(names):
             pos.setdefault(n, i)
+        cache[d] = (names, len(names), pos)
+        return pos
+
+    def index_of(self, wanted: Sequence[str], d: int) -> np.ndarray:
+        pos = self._positions(d)
         try:
             return np.array([pos[str(w)] for w in wanted], dtype=np.int32)
         except KeyError as e:

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-C5_WEIGHTED=1 C5_REPS=3 SS_RECSYS_VERBOSE=1 timeout 400 python tools/bench_c5.py 2000000 500000 0.05 > gpurun_out/c5_weighted.log 2>&1; echo "weighted exit $?"; tail -1 gpurun_out/c5_weighted.log | cut -c1-800
-cp gpurun_out/c5.json gpurun_out/c5_weighted.json
+timeout 400 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "cross_validate or alpha_sweep" > gpurun_out/pytest_cv.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_cv.log
+SS_SKIP_REFERENCE_FORMS=1 timeout 600 python tools/bench_configs.py > gpurun_out/configs_cv.log 2>&1; echo "configs exit $?"; head -1 gpurun_out/configs_cv.log | cut -c1-400
