@@ -675,6 +675,7 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
     else if (shape && !strcmp(shape, "6x1024")) st = SS_FUSED(6, 1024, 16);
     else if (shape && !strcmp(shape, "7x1024")) st = SS_FUSED(7, 1024, 16);
     else if (unit == 8) st = SS_FUSED(8, 1024, 8);
+    else if (unit == 32) st = SS_FUSED(8, 1024, 32);
     else st = SS_FUSED(8, 1024, 16);
 #undef SS_FUSED
     const bool big = shape && strcmp(shape, "8x1024");

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'jaccard_featurize_kernel|tanimoto_bits_kernel' -s 2 -c 2 \
-    -o gpurun_out/r01_similarity_ncu -f python tools/bench_similarity.py > gpurun_out/ncu_similarity.log 2>&1
-echo "ncu exit $?"
+export SS_RECSYS_VERBOSE=1 C5_REPS=3
+for u in 32 16; do
+SS_RECSYS_UNIT=$u timeout 300 python tools/bench_c5.py 2000000 500000 0.05 > gpurun_out/c5_unit$u.log 2>&1; echo "unit $u exit $?"; grep clusters gpurun_out/c5_unit$u.log | tail -1; tail -1 gpurun_out/c5_unit$u.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_all_reps'])"
+done
