@@ -67,17 +67,85 @@ def dims(scale: float):
 # ------------------------------------------------------------------------------------------------
 
 
-def cpu_reference_run(steps: int, warmup: int, sample_div: int = 20):
-    """Times `construct -> spread -> A*(W*W) -> slice` (reference src/core.jl:148-201, 365-371,
-    402-423) in NumPy/OpenBLAS on the host cores, on a 1/sample_div-scale replica of C4 (the literal
-    n x n path needs 289 GB per matrix at full size and cannot run).  Returns scores/s."""
+def host_threads() -> int:
+    """Host cores this process may use (the affinity mask, not os.cpu_count())."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def force_blas_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the CPU arm on one core.  The CPU arm
+    uses every host core it may run on: the environment is overridden (in case NumPy is not loaded yet) and the
+    BLAS pool is resized explicitly (in case it is).  Returns the thread count actually in use."""
+    n = host_threads()
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(n)
+    import numpy  # noqa: F401  (loads the BLAS whose pool is resized below)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        blas = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(blas)) if blas else n
+    except Exception:
+        return n
+
+
+def cpu_dgemm_rate(np, m: int = 2048) -> float:
+    """flop/s of the host BLAS on an m^3 DGEMM (used only to size the bounded sample)."""
+    a = np.random.default_rng(1).random((m, m))
+    best = 0.0
+    for _ in range(6):  # the BLAS pool needs a few calls to spin up after a resize
+        t0 = time.perf_counter()
+        a @ a
+        best = max(best, 2.0 * m ** 3 / (time.perf_counter() - t0))
+    return best
+
+
+def cpu_block_reduced_full_inner(np, threads: int):
+    """Block-reduced CPU form (T = (Xs' * (Y ./ ks)) ./ kf, R = Xq * T) in NumPy/OpenBLAS at the FULL
+    inner dimensions of C4 (Ns = Nf = 20 000), on a sample of query rows and target columns.  A score costs the same
+    flops here as in the full problem once the T product is charged per target column and the R product per score:
+    t_full = t_T * Nt / nt_s + t_R * (Nq * Nt) / (nq_s * nt_s).  A proxy for "a sane CPU implementation" -- the
+    reference itself runs the literal n x n path (timed as `value`)."""
+    ns = nf = C4["ns"]
+    nq_s, nt_s = 10_000, 2_500
+    rng = np.random.default_rng(SEED)
+    Xs = rng.random((ns, nf))
+    Xq = rng.random((nq_s, nf))
+    Y = (rng.random((ns, nt_s)) < C4["y_density"]).astype(np.float64)
+    t0 = time.perf_counter()
+    ks = np.count_nonzero(Xs, axis=1) + np.count_nonzero(Y, axis=1)
+    kf = np.count_nonzero(Xs, axis=0)
+    Wst = Y / np.maximum(ks, 1)[:, None]
+    T = (Xs.T @ Wst) / np.maximum(kf, 1)[:, None]
+    t_T = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    R = Xq @ T
+    t_R = time.perf_counter() - t0
+    del R
+    t_full = t_T * C4["nt"] / nt_s + t_R * (C4["nq"] * C4["nt"]) / (nq_s * nt_s)
+    return {"value": C4["nq"] * C4["nt"] / t_full, "unit": UNIT, "cores": threads,
+            "shape": f"Ns = Nf = {ns} (full), sample of {nq_s} query rows x {nt_s} target columns",
+            "t_T_s": t_T, "t_R_s": t_R, "extrapolated_full_step_s": t_full,
+            "note": "block-reduced NumPy/OpenBLAS chain at C4's full inner dimensions (48 000 flop per score as on "
+                    "the GPU); extrapolated linearly in target columns (T) and scores (R); NOT the reference's path"}
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 100.0, with_block_reduced: bool = True):
+    """Times `construct -> spread -> A*(W*W) -> slice -> clean!` (reference src/core.jl:148-201, 365-371, 402-423,
+    478-484) in NumPy/OpenBLAS on every host core, on a 1/div-scale replica of C4 (the literal n x n path needs
+    289 GB per matrix at full size and cannot run).  `div` is chosen from a DGEMM calibration so that the
+    warmup + steps passes fit `budget_s`.  Returns (cpu_baseline dict, seconds per step)."""
+    threads = force_blas_threads()
     import numpy as np
     from oracle import simspread_oracle as o
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
+    rate = cpu_dgemm_rate(np)
+    per_step = budget_s / max(1, steps + warmup)
+    n_full = C4["nq"] + C4["ns"] + C4["nf"] + C4["nt"]
+    n_fit = (0.6 * per_step * rate / 4.0) ** (1.0 / 3.0)       # literal path: two n^3 DGEMMs = 4 n^3 flop
+    sample_div = int(min(80, max(16, -(-n_full // max(1.0, n_fit)))))
     nq, ns, nf, nt = (C4["nq"] // sample_div, C4["ns"] // sample_div, C4["nf"] // sample_div,
                       C4["nt"] // sample_div)
     Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=SEED, y_density=C4["y_density"], alpha=C4["alpha"],
@@ -103,22 +171,27 @@ def cpu_reference_run(steps: int, warmup: int, sample_div: int = 20):
         times.append(time.perf_counter() - t0)
     t = statistics.median(times)
     n = nq + ns + nf + nt
-    t0 = time.perf_counter()
-    o.predict_blocks_query(Xq, Xs, Y)
-    t_blocks = time.perf_counter() - t0
-    return {
+    base = {
         "value": nq * nt / t, "unit": UNIT, "cores": int(threads), "kind": "port",
         "sample": f"1/{sample_div}-scale C4 replica (nq={nq}, ns=nf={ns}, nt={nt}; dense n={n}), literal "
-                  f"NumPy/OpenBLAS restatement of construct+spread+A*(W*W)+clean!, median of {steps}; "
-                  "Julia is not installed, this is a port not SimSpread.jl itself",
+                  f"NumPy/OpenBLAS restatement of construct+spread+A*(W*W)+clean!, median of {steps}, {threads} BLAS "
+                  f"threads (host DGEMM {rate / 1e9:.0f} GFLOP/s); Julia is not installed, this is a port not "
+                  "SimSpread.jl itself",
         "seconds_per_step": t,
-        "block_reduced_value": nq * nt / t_blocks,
-    }, t
+    }
+    if with_block_reduced:
+        try:
+            base["block_reduced"] = cpu_block_reduced_full_inner(np, threads)
+            base["block_reduced_value"] = base["block_reduced"]["value"]
+        except MemoryError:
+            base["block_reduced"] = {"error": "not enough host memory for the full-inner-dimension sample"}
+    return base, t
 
 
 def cpu_reference_small_configs(which: str):
     """The reference's literal CPU path (dense n x n construct -> spread -> A*(W*W) -> clean!) on BASELINE config 2
     (Enzyme-shaped, all 10 folds) or on ONE alpha of config 3 (n = 17 000; the dense DGEMMs do not depend on alpha)."""
+    threads = force_blas_threads()
     import numpy as np
     from oracle import simspread_oracle as o
     rng = np.random.default_rng(20241)
@@ -148,7 +221,7 @@ def cpu_reference_small_configs(which: str):
         o.clean(w, Ao, nn, tn)
         n_full = Ao.shape[0]
     t = time.perf_counter() - t0
-    return {"value": nq_total * Nt / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": nq_total * Nt / t, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{which}: literal NumPy/OpenBLAS restatement of featurize + construct + spread + A*(W*W) + clean!, "
                       f"{len(folds)} fold(s), dense n = {n_full}", "seconds_per_step": t}, t
 
@@ -481,7 +554,7 @@ def run_b200(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu, _ = cpu_reference_run(steps=3, warmup=1)
+            cpu, _ = cpu_reference_run(steps=3, warmup=1, budget_s=30.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
