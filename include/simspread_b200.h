@@ -74,6 +74,7 @@ typedef struct ss_ctx ss_ctx;   /* one GPU + one stream + workspaces */
 typedef struct ss_mat ss_mat;   /* dense float64 column-major device matrix */
 typedef struct ss_ivec ss_ivec; /* int32 device vector (degrees, index lists) */
 typedef struct ss_csr ss_csr;   /* CSR device matrix (int32 row_ptr/col_idx, optional f64 values) */
+typedef struct ss_transfer ss_transfer; /* item x item block of W*W of a 2-layer graph, split by column tile */
 
 /* ---- library / context ------------------------------------------------------------------- */
 SS_API int32_t ss_version(void);
@@ -235,6 +236,21 @@ SS_API int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y,
  * indices, -1 padding), val_out (optional) the matching scores, an L x sources matrix.  L <= 32. */
 SS_API int32_t ss_recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int32_t L, int64_t s_begin,
                                  int64_t s_end, ss_ivec* idx_out, ss_mat* val_out);
+/* The same computation in two steps, for callers that rank several source ranges of one graph (multi-GPU
+ * sharding, repeated calls): ss_transfer_build materialises U = (W*W)[targets, targets] =
+ * (Y' ./ kt) * (Y ./ ks) of the reference's `Aarr * Warr^2` [src/core.jl:456] once -- rows sorted by column,
+ * split by column tile, every entry summed in ascending source order -- and ss_recommend_topl_transfer streams
+ * it: F[s,:] = sum_{t' in Y[s,:], ascending} Y[s,t'] * U[t',:] accumulated in shared memory (no atomics: scores
+ * and the order of tied scores are reproducible bit for bit), reduced to the top L.  ss_recommend_topl does both
+ * and falls back to column-tile chunks when U does not fit in the free device memory.
+ * ss_transfer_info: info4 = {entries of U, device bytes, tile width, column tiles}.
+ * ss_transfer_download (tests): U as a host CSR (row_ptr: targets + 1 int64, global int32 columns, values). */
+SS_API int32_t ss_transfer_build(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, ss_transfer** out);
+SS_API int32_t ss_transfer_info(const ss_transfer* U, int64_t* info4);
+SS_API int32_t ss_transfer_download(const ss_transfer* U, int64_t* row_ptr_host, int32_t* col_host, double* val_host);
+SS_API int32_t ss_transfer_destroy(ss_transfer* U);
+SS_API int32_t ss_recommend_topl_transfer(ss_ctx* ctx, const ss_csr* Y, const ss_transfer* U, int32_t L, int64_t s_begin,
+                                          int64_t s_end, ss_ivec* idx_out, ss_mat* val_out);
 /* clean! [src/core.jl:478-484]: R[:,t] = -99 for every t with kt[t] == 0. */
 SS_API int32_t ss_clean(ss_ctx* ctx, ss_mat* R, const ss_ivec* kt);
 

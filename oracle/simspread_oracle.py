@@ -304,6 +304,86 @@ def predict_blocks_source(Xs: np.ndarray, Y: np.ndarray) -> np.ndarray:
     return Xs @ (Wfs @ Wst) + Y @ (Wts @ Wst)
 
 
+def two_layer_transfer_loops(Y: np.ndarray):
+    """Item x item block of `W^2` for the 2-layer graph `[0 Y; Y' 0]` (BASELINE config 5), literal loops in the
+    order the reference's association fixes: `Aarr * Warr^2` (src/core.jl:456) squares W = G ./ k (src/core.jl:366)
+    first, so U[t',t] = sum over sources s' (ascending) of fl(Y[s',t']/kt[t']) * fl(Y[s',t]/ks[s']), every product
+    and every addition rounded on its own.  Small cases only (pure Python).  Returns the dense U."""
+    Y = np.asarray(Y, dtype=np.float64)
+    ns, nt = Y.shape
+    ks = np.count_nonzero(Y != 0, axis=1)
+    kt = np.count_nonzero(Y != 0, axis=0)
+    U = np.zeros((nt, nt))
+    for tp in range(nt):
+        for sp in range(ns):
+            if Y[sp, tp] == 0:
+                continue
+            w1 = Y[sp, tp] / float(kt[tp])
+            for t in range(nt):
+                if Y[sp, t] != 0:
+                    U[tp, t] = U[tp, t] + w1 * (Y[sp, t] / float(ks[sp]))
+    return U
+
+
+def two_layer_scores_loops(Y: np.ndarray) -> np.ndarray:
+    """F = Y * U in ascending t' order, F[s,t] = sum_{t' asc} Y[s,t'] * U[t',t] (rows of `Aarr * (Warr^2)` that belong
+    to the sources; src/core.jl:456, 464).  Small cases only."""
+    Y = np.asarray(Y, dtype=np.float64)
+    U = two_layer_transfer_loops(Y)
+    ns, nt = Y.shape
+    F = np.zeros((ns, nt))
+    for s in range(ns):
+        for tp in range(nt):
+            if Y[s, tp] != 0:
+                nzc = np.nonzero(U[tp])[0]
+                F[s, nzc] = F[s, nzc] + Y[s, tp] * U[tp, nzc]
+    return F
+
+
+def two_layer_scores_sparse(Y, rows=None):
+    """The same sums with scipy.sparse (CSR x CSR Gustavson products add in ascending inner index when the rows are
+    sorted, multiply and add rounded separately): U = (Y' ./ kt) * (Y ./ ks), F = Y[rows] * U.  `Y`: dense array or
+    scipy sparse matrix (sources x targets).  Returns (F as CSR restricted to `rows`, U as CSR)."""
+    import scipy.sparse as sp
+    Yc = sp.csr_matrix(Y, dtype=np.float64)
+    Yc.eliminate_zeros()
+    Yc.sort_indices()
+    ks = np.diff(Yc.indptr).astype(np.float64)
+    Yt = Yc.T.tocsr()
+    Yt.sort_indices()
+    kt = np.diff(Yt.indptr).astype(np.float64)
+    Wst = Yc.copy()
+    Wst.data = Wst.data / np.repeat(ks, np.diff(Yc.indptr))   # true division per element (src/core.jl:366)
+    Wts = Yt.copy()
+    Wts.data = Wts.data / np.repeat(kt, np.diff(Yt.indptr))
+    if rows is None:
+        U = Wts @ Wst
+        return Yc @ U, U
+    # only the rows of U that the requested sources reach (the item order, hence the order of additions, is kept)
+    A = Yc[np.asarray(rows)]
+    need = np.unique(A.indices)
+    U = Wts[need] @ Wst
+    A_sub = sp.csr_matrix((A.data, np.searchsorted(need, A.indices), A.indptr), shape=(A.shape[0], need.size))
+    return A_sub @ U, U
+
+
+def recommend_topl(Y, L: int, rows=None):
+    """Top-L targets per source under `sortperm(rev=true)` (src/performance.jl:315) of the scores above.
+    Returns (idx (n, L) int64, val (n, L))."""
+    F, _ = two_layer_scores_sparse(Y, rows)
+    n, nt = F.shape
+    idx = np.zeros((n, L), dtype=np.int64)
+    val = np.zeros((n, L))
+    for i in range(n):
+        row = np.zeros(nt)
+        sl = slice(F.indptr[i], F.indptr[i + 1])
+        row[F.indices[sl]] = F.data[sl]
+        o = sortperm_rev(row)[:L]
+        idx[i] = o
+        val[i] = row[o]
+    return idx, val
+
+
 def clean_blocks(R: np.ndarray, kt_full: np.ndarray) -> None:
     """`clean!` (src/core.jl:478-484) in block form: kt_full = degree of each target row of A
     (= nnz of the target's column in the source-target block; query rows have no target edges)."""

@@ -68,6 +68,11 @@ SIGNATURES = {
     "ss_csr_destroy": (c_i32, [vp]),
     "ss_csr_wrap": (c_i32, [vp, c_i64, c_i64, c_i64, vp, vp, vp, P(vp)]),
     "ss_recommend_topl": (c_i32, [vp, vp, vp, c_i32, c_i64, c_i64, vp, vp]),
+    "ss_transfer_build": (c_i32, [vp, vp, vp, P(vp)]),
+    "ss_transfer_info": (c_i32, [vp, vp]),
+    "ss_transfer_download": (c_i32, [vp, vp, vp, vp]),
+    "ss_transfer_destroy": (c_i32, [vp]),
+    "ss_recommend_topl_transfer": (c_i32, [vp, vp, vp, c_i32, c_i64, c_i64, vp, vp]),
     "ss_gather": (c_i32, [vp, vp, vp, vp, vp]),
     "ss_degrees": (c_i32, [vp, vp, vp, vp, vp, vp]),
     "ss_k_rows": (c_i32, [vp, vp, vp]),

@@ -132,6 +132,8 @@ int32_t auroc_auprc(ss_ctx* ctx, const uint8_t* labels, const double* scores, in
 int32_t auroc_auprc_mat(ss_ctx* ctx, const ss_mat* Y, const ss_mat* R, double* out2);
 int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
                        int32_t* idx_out, double* val_out, int64_t ldv);
+int32_t recommend_topl_stream(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
+                              int32_t* idx_out, double* val_out, int64_t ldv, bool* declined);
 int32_t jaccard_featurize(ss_ctx* ctx, const ss_mat* A, const ss_mat* B, double alpha, bool weighted, ss_mat* X);
 int32_t tanimoto_bits_featurize(ss_ctx* ctx, const uint64_t* FA, int64_t na, const uint64_t* FB, int64_t nb, int64_t words,
                                 double alpha, bool weighted, ss_mat* X);

@@ -641,8 +641,19 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
                        int32_t* idx_out, double* val_out, int64_t ldv) {
     const int64_t nt = Y->cols;
     if (s_end <= s_begin || nt == 0) return SS_OK;
-    const char* mode = getenv("SS_RECSYS_MODE");  // "groups": force the three-kernel form (debugging / A-B runs)
-    if (mode && !strcmp(mode, "groups")) return recommend_groups(ctx, Y, YT, L, s_begin, s_end, nullptr, idx_out, val_out, ldv);
+    // default: the deterministic shared-memory form over the materialised transfer matrix (ss_transfer.cu).
+    // SS_RECSYS_MODE = "atomic": the round-1 cluster kernel below (two-hop expansion, red.global.add.f64 into
+    // L2-resident rows; sums in no fixed order); "groups": its three-kernel predecessor.  Both kept for A/B runs.
+    // A graph whose transfer matrix cannot be materialised (heavy-tailed degrees: it approaches items x items) is
+    // declined by that form and also takes the cluster kernel.
+    const char* mode = getenv("SS_RECSYS_MODE");
+    if (!mode || (strcmp(mode, "atomic") && strcmp(mode, "groups"))) {
+        bool declined = false;
+        SS_TRY(recommend_topl_stream(ctx, Y, YT, L, s_begin, s_end, idx_out, val_out, ldv, &declined));
+        if (!declined) return SS_OK;
+    } else if (!strcmp(mode, "groups")) {
+        return recommend_groups(ctx, Y, YT, L, s_begin, s_end, nullptr, idx_out, val_out, ldv);
+    }
     const bool weighted = Y->values != nullptr;
     const int64_t ldacc = round_up(nt, 32);
     FusedParams fp{};

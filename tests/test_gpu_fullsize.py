@@ -206,3 +206,70 @@ def test_full_size_ranking_metric_properties(env):
     assert bool(ties_in_order.all())
     kth = torch.topk(R[:2000], Ltop, dim=1).values
     assert bool(torch.equal(kth, vals[:2000]))
+
+
+@pytest.mark.parametrize("degrees,weighted", [("poisson", False), ("poisson", True), ("pareto", False)])
+def test_c5_full_size_graph_user_slice_against_scipy(env, degrees, weighted):
+    """BASELINE config 5 at FULL graph size (2M users x 500k items, ~1e8 edges): the transfer matrix U of the whole
+    graph is built on the device and a slice of the users is ranked; sampled users are recomputed with scipy.sparse
+    (CSR x CSR products add in the same ascending order, oracle/simspread_oracle.py): the top-20 columns must equal
+    `sortperm(rev=true)[1:20]` row for row and the scores bit for bit -- binary graphs tie everywhere, so this is the
+    north star's "bit-exact top-k order" where it is hardest -- and a second run must return identical bits.
+    The Pareto-degree variant (users with up to 20 000 items) has a transfer matrix that approaches items x items: it is
+    declined by the materialised form, `ss_recommend_topl` takes the two-hop expansion kernel (unordered FP64 sums), and
+    the check is the FP64 tolerance plus the order wherever the scores differ."""
+    import os
+    import sys
+    import scipy.sparse as sp
+    from oracle import simspread_oracle as o
+    ss, check, ctx, torch, dev, L = (env[k] for k in ("ss", "check", "ctx", "torch", "dev", "L"))
+    if env["free_gb"] < 100:
+        pytest.skip("needs ~70 GB of device memory")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from c5_graph import make_graph, wrap
+    ns, nt, topl = 2_000_000, 500_000, 20
+    G = make_graph(ns, nt, 1e-4, dev, degrees, weighted)
+    hY, hYT = wrap(L, ctx, check, G)
+    exact = degrees == "poisson"
+    users = 20_000 if exact else 2_000  # a slice of the users; U is that of the whole graph
+    idx = torch.full((ns, topl), -2, dtype=torch.int32, device=dev)
+    val = torch.zeros((ns, topl), dtype=torch.float64, device=dev)
+    vi, vm = C.c_void_p(), C.c_void_p()
+    check(L.ss_ivec_wrap(ctx.h, C.c_void_p(idx.data_ptr()), ns * topl, C.byref(vi)))
+    check(L.ss_mat_wrap(ctx.h, C.c_void_p(val.data_ptr()), topl, ns, topl, C.byref(vm)))
+    s0 = 1_000_000
+    if exact:
+        hU = C.c_void_p()
+        check(L.ss_transfer_build(ctx.h, hY, hYT, C.byref(hU)))
+        try:
+            check(L.ss_recommend_topl_transfer(ctx.h, hY, hU, topl, s0, s0 + users, vi, vm))
+            i1, v1 = idx[s0:s0 + users].clone(), val[s0:s0 + users].clone()
+            idx[s0:s0 + users] = -2
+            check(L.ss_recommend_topl_transfer(ctx.h, hY, hU, topl, s0, s0 + users, vi, vm))
+            assert torch.equal(i1, idx[s0:s0 + users]) and torch.equal(v1.view(torch.int64), val[s0:s0 + users].view(torch.int64))
+        finally:
+            check(L.ss_transfer_destroy(hU))
+    else:
+        check(L.ss_recommend_topl(ctx.h, hY, hYT, topl, s0, s0 + users, vi, vm))
+        i1, v1 = idx[s0:s0 + users].clone(), val[s0:s0 + users].clone()
+    assert int(idx[:s0].max()) == -2 and int(idx[s0 + users:].max()) == -2   # rows outside the range are untouched
+    # oracle on sampled users of the slice (host: the graph as scipy CSR)
+    data = (G["y_val"] if weighted else torch.ones(G["nnz"], dtype=torch.float64, device=dev)).cpu().numpy()
+    Ysp = sp.csr_matrix((data, G["y_idx"].cpu().numpy(), G["y_ptr"].cpu().numpy()), shape=(ns, nt))
+    rng = np.random.default_rng(3)
+    deg = np.diff(Ysp.indptr[s0:s0 + users + 1])
+    cand = np.flatnonzero(deg <= 200)  # the oracle needs the rows of U these users reach: keep it in host memory
+    rows = np.sort(rng.choice(cand, size=48 if exact else 12, replace=False)) + s0
+    F, _ = o.two_layer_scores_sparse(Ysp, rows)
+    got_i, got_v = i1.cpu().numpy(), v1.cpu().numpy()
+    for j, r in enumerate(rows):
+        dense = np.zeros(nt)
+        sl = slice(F.indptr[j], F.indptr[j + 1])
+        dense[F.indices[sl]] = F.data[sl]
+        order = o.sortperm_rev(dense)[:topl]
+        if exact:
+            assert np.array_equal(got_i[r - s0], order), (degrees, weighted, int(r))
+            assert np.array_equal(got_v[r - s0].view(np.uint64), dense[order].view(np.uint64)), (degrees, weighted, int(r))
+        else:
+            assert np.allclose(got_v[r - s0], dense[order], rtol=1e-12, atol=0.0), (degrees, int(r))
+            assert np.allclose(dense[got_i[r - s0]], dense[order], rtol=1e-12, atol=0.0), (degrees, int(r))
