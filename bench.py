@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip e2e_api and the side configs (C2 / C3 / C5)")
     return ap.parse_args()
 
 
@@ -188,11 +189,9 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 100.0, with_blo
     return base, t
 
 
-def cpu_reference_small_configs(which: str):
-    """The reference's literal CPU path (dense n x n construct -> spread -> A*(W*W) -> clean!) on BASELINE config 2
-    (Enzyme-shaped, all 10 folds) or on ONE alpha of config 3 (n = 17 000; the dense DGEMMs do not depend on alpha)."""
-    threads = force_blas_threads()
-    import numpy as np
+def synth_small_config(np, which: str):
+    """BASELINE config 2 (Enzyme-shaped: 445 x 664, Beta(2,5) similarities, binary alpha = 0.35, 10 folds) or config 3
+    (5 000 queries + 5 000 sources x 2 000 targets, uniform similarities, weighted); seeded."""
     from oracle import simspread_oracle as o
     rng = np.random.default_rng(20241)
     if which == "C2":
@@ -202,7 +201,6 @@ def cpu_reference_small_configs(which: str):
         Y = (rng.random((N, Nt)) < 0.0099).astype(float)
         names = [f"D{i:04d}" for i in range(N)]
         folds = o.split_round_robin([names[i] for i in rng.permutation(N)], 10)
-        nq_total = N
     else:
         nq, ns, Nt, alpha, weighted = 5000, 5000, 2000, 0.5, True
         N = nq + ns
@@ -210,8 +208,18 @@ def cpu_reference_small_configs(which: str):
         Y = (rng.random((N, Nt)) < 0.01).astype(float)
         names = [f"n{i}" for i in range(N)]
         folds = [names[:nq]]
-        nq_total = nq
     tn = [f"t{j}" for j in range(Nt)]
+    return S, Y, names, tn, folds, alpha, weighted
+
+
+def cpu_reference_small_configs(which: str):
+    """The reference's literal CPU path (dense n x n construct -> spread -> A*(W*W) -> clean!) on BASELINE config 2
+    (Enzyme-shaped, all 10 folds) or on ONE alpha of config 3 (n = 17 000; the dense DGEMMs do not depend on alpha)."""
+    threads = force_blas_threads()
+    import numpy as np
+    from oracle import simspread_oracle as o
+    S, Y, names, tn, folds, alpha, weighted = synth_small_config(np, which)
+    nq_total, Nt = sum(len(f) for f in folds), len(tn)
     t0 = time.perf_counter()
     Xo, xr, xc = o.featurize(S, names, names, alpha, weighted)
     n_full = 0
@@ -412,12 +420,21 @@ def run_b200(args):
     bR, ldr = colmajor(torch, nq_l, nt, dev)
     mR = ss.DMat.wrap(ctx, bR.data_ptr(), nq_l, nt, ldr)
 
-    sharded = None
+    # N > 1: every exchange step lives behind the C ABI (ss_comm_* / ss_predict_query_sharded: NCCL dlopen()ed by the
+    # library, T tiles stored into the peers from the GEMM epilogue).  torch.distributed only launched the ranks and
+    # carries the 128-byte NCCL unique id to them.
+    sharded = comm = None
     if world > 1:
-        from simspread_b200.sharded import LibBackend, ShardedPredict, make_plan
-        plan = make_plan(nq, nt, world, rank)
-        sharded = ShardedPredict(plan, LibBackend(ss, ctx, torch, dist, plan, ns, nf, bXq, ldq, bXs, lds, bY, ldy,
-                                                  bR, ldr))
+        from simspread_b200.sharded import Comm, ShardedQuery
+
+        def exchange(raw: bytes) -> bytes:
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        comm = Comm(ctx, rank, world, exchange=exchange)
+        sharded = ShardedQuery(comm, ns, nf, nt)
+        assert sharded.nt_blk == nt_l
 
     ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
@@ -429,14 +446,13 @@ def run_b200(args):
         if world == 1:
             check(L.ss_predict_query(ctx.h, mXq.h, mXs.h, mY.h, mR.h, SS_PREDICT_CLEAN | pflag, None))
         else:
-            sharded.step(clean=True)
+            sharded.predict(mXq, mXs, mY, mR, clean=True)
 
     def barrier():
         ctx.sync()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+            comm.barrier()
 
     for _ in range(args.warmup):
         step()
@@ -456,9 +472,7 @@ def run_b200(args):
     ctx.profile(False)
     launches = ctx.launch_count() - launches0
     if world > 1:
-        t_ = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        ms_total = float(t_.item())
+        ms_total = comm.allreduce_host([ms_total], "max")[0]
     ms_step = ms_total / args.steps
     value = nq * nt / (ms_step * 1e-3)
 
@@ -514,13 +528,15 @@ def run_b200(args):
         checkres = {"sampled_entries": 64, "max_rel_err": rel, "tolerance": tol, "ok": bool(rel < tol)}
 
     if not args.no_check and world > 1:
-        # (i) every rank must hold the same all-gathered T; (ii) entries of this rank's R slab whose
-        # target column lies in this rank's Y block are recomputed with torch/cuBLAS + torch collectives
-        be = sharded.b
-        cs = be.bT.sum().reshape(1)
-        allcs = [torch.zeros_like(cs) for _ in range(world)]
-        dist.all_gather(allcs, cs)
-        same_T = all(bool(torch.equal(allcs[0], c)) for c in allcs)
+        # (i) every rank must hold the same assembled T; (ii) entries of this rank's R slab whose target column lies
+        # in this rank's Y block are recomputed with torch/cuBLAS (torch.distributed only sums the checker's degrees)
+        from simspread_b200.sharded import _CudaView
+        hT, _hk = sharded.views()
+        tr_, tc_, tld_, tp_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_void_p()
+        check(L.ss_mat_info(hT, C.byref(tr_), C.byref(tc_), C.byref(tld_), C.byref(tp_)))
+        bT = torch.as_tensor(_CudaView(tp_.value, (tc_.value, tld_.value)), device=dev)[:, :nf]
+        cs = comm.allreduce_host([float(bT.sum().item()), -float(bT.sum().item())], "max")
+        same_T = bool(cs[0] == -cs[1])  # max(x) == min(x) over the ranks
         g = torch.Generator(device="cpu")
         g.manual_seed(11 + rank)
         tq = torch.randint(0, nq_l, (32,), generator=g).to(dev)
@@ -537,15 +553,15 @@ def run_b200(args):
         want = (bXq[:, :nq_l].T[tq] * Tcols.T).sum(1)
         want = torch.where(kt_[tl] == 0, torch.full_like(want, -99.0), want)
         got = bR[tl + t0, tq]
-        rel = ((got - want).abs() / want.abs().clamp_min(1e-300)).max().reshape(1)
-        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
-        checkres = {"sampled_entries": 32 * world, "max_rel_err": float(rel.item()), "tolerance": 1e-12,
-                    "ok": bool(rel.item() < 1e-12 and same_T), "all_ranks_hold_identical_T": same_T}
+        rel = float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item())
+        rel = comm.allreduce_host([rel], "max")[0]
+        checkres = {"sampled_entries": 32 * world, "max_rel_err": rel, "tolerance": 1e-12,
+                    "ok": bool(rel < 1e-12 and same_T), "all_ranks_hold_identical_T": same_T}
 
     # ---- e2e: reference-facing host-buffer call, H2D/D2H inside the timed region ----------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq, bXs, bY, ldq, lds, ldy,
+        e2e = run_e2e(args, ss, ctx, torch, comm, np, dev, world, rank, d, nq_l, nt_l, bXq, bXs, bY, ldq, lds, ldy,
                       sharded,
                       (mXq, mXs, mY, mR, bR, ldr))
 
@@ -565,7 +581,8 @@ def run_b200(args):
                        "sharding": "single GPU" if world == 1 else
                        (f"query rows x{world}; T by target-column block, " +
                         ("blocks stored to all peers from the T-GEMM epilogue over NVLink P2P (fused all-gather)"
-                         if sharded.b.mirrors is not None else "NCCL all-gather")),
+                         if sharded.fused else "NCCL all-gather") +
+                        f"; collectives behind the C ABI (ss_comm_*, NCCL {comm.nccl_version()} dlopen()ed by the library)"),
                        "l2": "inputs (27 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "check": checkres, "opt_in_f64_int8": None,
@@ -613,12 +630,214 @@ def run_b200(args):
             line["opt_in_f64_int8"] = {"error": f"{type(exc).__name__}: {exc}"}
         dog.cancel()
 
+    # ---- the call a user makes (NamedArrays in pageable memory) and the other BASELINE configs, beside the headline
+    if world == 1 and not pflag and not args.no_side:
+        import threading
+
+        def _bail2():
+            line.setdefault("side_configs", {"error": "the side measurements did not finish within 420 s; not reported"})
+            print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(420.0, _bail2)
+        dog.daemon = True
+        dog.start()
+        del bXq, bR, mXq, mR
+        torch.cuda.empty_cache()
+        try:
+            line["e2e_api"] = run_e2e_api(ss, np, d)
+        except Exception as exc:  # noqa: BLE001
+            line["e2e_api"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            del bXs, bY, mXs, mY
+            torch.cuda.empty_cache()
+            line["side_configs"] = run_side_configs(ss, np, torch, ctx, dev)
+        except Exception as exc:  # noqa: BLE001
+            line["side_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
+        dog.cancel()
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        sharded.close()
+        comm.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_e2e_api(ss, np, d, nq_api=10_000):
+    """The call a user makes: construct((ytrain, ytest), (Xtrain, Xtest)) + predict((A, B), ytest, clean=True) on
+    NamedArrays that live in ordinary (pageable) NumPy memory, result back as a NamedArray; C4's inner dimensions with
+    `nq_api` queries.  Beside it the C entry point (`ss_predict_query_host`, pinned buffers) on the same shape."""
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    ns, nf, nt = d["ns"], d["nf"], d["nt"]
+    rng = np.random.default_rng(SEED + 7)
+    Xs = np.asfortranarray(np.round(rng.random((ns, nf)), 6))
+    Xq = np.asfortranarray(np.round(rng.random((nq_api, nf)), 6))
+    Y = np.asfortranarray((rng.random((ns, nt)) < d["y_density"]).astype(np.float64))
+    Yq = np.zeros((nq_api, nt), order="F")
+    sn, qn = [f"s{i}" for i in range(ns)], [f"q{i}" for i in range(nq_api)]
+    fn, tn = [f"f{i}" for i in range(nf)], [f"t{i}" for i in range(nt)]
+    ytrain, ytest = ss.NamedArray(Y, (sn, tn)), ss.NamedArray(Yq, (qn, tn))
+    Xtrain, Xtest = ss.NamedArray(Xs, (sn, fn)), ss.NamedArray(Xq, (qn, fn))
+
+    def api_step():
+        A, B = ss.construct((ytrain, ytest), (Xtrain, Xtest))
+        return ss.predict((A, B), ytest, clean=True, layout="dense")
+
+    got = api_step()  # warm-up
+    t0 = time.perf_counter()
+    got = api_step()
+    t_api = time.perf_counter() - t0
+    # the C entry point on the same shape, pinned buffers
+    ctx, L = ss.Context.default(), ss.lib()
+    R = np.empty((nq_api, nt), order="F")
+    ptrs = []
+    for a in (Xq, Xs, Y, R):
+        p = C.c_void_p()
+        check(L.ss_host_alloc(a.size * 8, C.byref(p)))
+        ptrs.append(p)
+        if a is not R:
+            C.memmove(p, a.ctypes.data, a.size * 8)
+    pXq, pXs, pY, pR = ptrs
+    call = lambda: check(L.ss_predict_query_host(ctx.h, pXq, nq_api, pXs, ns, pY, ns, nq_api, ns, nf, nt, SS_PREDICT_CLEAN, pR, nq_api))
+    call()
+    t0 = time.perf_counter()
+    call()
+    t_entry = time.perf_counter() - t0
+    Rn = np.ctypeslib.as_array(C.cast(pR, C.POINTER(C.c_double)), shape=(nt, nq_api)).T
+    same = bool(np.array_equal(got.array, Rn))
+    for p in ptrs:
+        L.ss_host_free(p)
+    return {"value": nq_api * nt / t_api, "unit": UNIT, "queries": nq_api, "ms": t_api * 1e3,
+            "h2d_bytes": int((Xq.size + Xs.size + Y.size) * 8), "d2h_bytes": int(nq_api * nt * 8),
+            "api": "construct((ytrain, ytest), (Xtrain, Xtest)) + predict((A, B), ytest, clean=True) on pageable NumPy NamedArrays",
+            "entry_point_same_shape": {"value": nq_api * nt / t_entry, "ms": t_entry * 1e3, "api": "ss_predict_query_host, pinned buffers"},
+            "ratio_api_over_entry_point": t_entry / t_api, "bit_identical_to_entry_point": same}
+
+
+def run_side_configs(ss, np, torch, ctx, dev):
+    """The other BASELINE configs on this GPU, each with its own check against the oracle (untimed): C2 = Enzyme-shaped
+    10-fold CV, C3 = 21-point weighted alpha sweep, C5 = sparse recommender (5 % of the users of the 2M x 500k graph).
+    Reported beside the headline; not part of `value`."""
+    import ctypes
+    from oracle import simspread_oracle as o
+    from simspread_b200._lib import check
+    out = {}
+    L = ss.lib()
+    # ---- C2 -----------------------------------------------------------------------------------------------------
+    S, Y, names, tn, folds, alpha, weighted = synth_small_config(np, "C2")
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Y, (names, tn))
+    ss.cross_validate(DT, DD, alpha, weighted=weighted, folds=folds)
+    ts, launches = [], 0
+    for _ in range(5):
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        res = ss.cross_validate(DT, DD, alpha, weighted=weighted, folds=folds)
+        ts.append(time.perf_counter() - t0)
+        launches = ctx.launch_count() - l0
+    Xo, xr, xc = o.featurize(S, names, names, alpha, weighted)
+    worst, row = 0.0, 0
+    for q in folds:
+        qi = [names.index(x) for x in q]
+        si = [i for i in range(len(names)) if names[i] not in set(q)]
+        Xq_, Xs_, Y_ = Xo[np.ix_(qi, si)], Xo[np.ix_(si, si)], Y[si]
+        want = o.predict_blocks_query(Xq_, Xs_, Y_)
+        o.clean_blocks(want, o.degrees_blocks(Xs_, Y_)[2])
+        got = res["yhat"].array[row:row + len(q)]
+        row += len(q)
+        nz = want != 0
+        if nz.any():
+            worst = max(worst, float(np.max(np.abs(got[nz] - want[nz]) / np.abs(want[nz]))))
+        if not np.array_equal(got[~nz], want[~nz]):
+            worst = float("inf")
+    yb = np.concatenate([Y[[names.index(x) for x in q]] for q in folds]).ravel() > 0
+    out["C2_enzyme_10fold_cv"] = {
+        "shape": [len(names), len(tn)], "alpha": alpha, "weighted": weighted, "ms_per_cv_wall_median_of_5": float(np.median(ts)) * 1e3,
+        "scores_per_s": len(names) * len(tn) / float(np.median(ts)), "kernel_launches_per_cv": int(launches),
+        "includes": "upload, featurize, 10 folds (gather, degrees, spread, T, R + clean!), AuROC/AuPRC, @20 metrics, download",
+        "check": {"max_rel_err_vs_oracle_block_form": worst, "tolerance": 1e-12,
+                  "AuROC_rel_diff_vs_oracle": abs(res["AuROC"] - o.AuROC(yb, res["yhat"].array.ravel())) / max(res["AuROC"], 1e-300),
+                  "ok": bool(worst < 1e-12)}}
+    # ---- C3 -----------------------------------------------------------------------------------------------------
+    S, Y, names, tn, folds, _, weighted = synth_small_config(np, "C3")
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Y, (names, tn))
+    q = folds[0]
+    alphas = [round(0.05 * i, 2) for i in range(21)]
+    ss.alpha_sweep(DT, DD, q, alphas[:2])
+    tm = {}
+    t0 = time.perf_counter()
+    sw = ss.alpha_sweep(DT, DD, q, alphas, timing=tm)
+    t_sw = time.perf_counter() - t0
+    a_chk = 0.5
+    nq = len(q)
+    Xo = o.cutoff(S[:, nq:], a_chk, True)
+    want = o.predict_blocks_query(Xo[:nq], Xo[nq:], Y[nq:])
+    o.clean_blocks(want, o.degrees_blocks(Xo[nq:], Y[nq:])[2])
+    au_want = o.AuROC(Y[:nq].ravel() > 0, want.ravel())
+    pt = [p_ for p_ in sw if abs(p_["alpha"] - a_chk) < 1e-9][0]
+    out["C3_alpha_sweep_21_points"] = {
+        "shape": {"nq": nq, "ns": len(names) - nq, "nt": len(tn)}, "wall_s": t_sw, "setup_s": tm.get("setup_s"),
+        "sweep_s": tm.get("sweep_s"), "ms_per_alpha": (tm.get("sweep_s") or t_sw) / 21 * 1e3, "scores_per_s": 21 * nq * len(tn) / t_sw,
+        "layouts": [p_.get("layout") for p_ in sw],
+        "check": {"alpha": a_chk, "AuROC": pt["AuROC"], "AuROC_oracle_block_form": au_want,
+                  "rel_diff": abs(pt["AuROC"] - au_want) / au_want, "tolerance": 1e-12, "ok": bool(abs(pt["AuROC"] - au_want) <= 1e-12 * au_want)}}
+    del DD, DT, S, Y
+    # ---- C5 -----------------------------------------------------------------------------------------------------
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from c5_graph import make_graph, partial_products, wrap
+    import scipy.sparse as sp
+    ns, nt, topl, frac = 2_000_000, 500_000, 20, 0.05
+    G = make_graph(ns, nt, 1e-4, dev, "poisson", False)
+    hY, hYT = wrap(L, ctx, check, G)
+    idx = torch.full((ns, topl), -2, dtype=torch.int32, device=dev)
+    val = torch.zeros((ns, topl), dtype=torch.float64, device=dev)
+    vi, vm = ctypes.c_void_p(), ctypes.c_void_p()
+    check(L.ss_ivec_wrap(ctx.h, ctypes.c_void_p(idx.data_ptr()), ns * topl, ctypes.byref(vi)))
+    check(L.ss_mat_wrap(ctx.h, ctypes.c_void_p(val.data_ptr()), topl, ns, topl, ctypes.byref(vm)))
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    hU = ctypes.c_void_p()
+    e0.record(ext)
+    check(L.ss_transfer_build(ctx.h, hY, hYT, ctypes.byref(hU)))
+    e1.record(ext)
+    users = int(ns * frac)
+    check(L.ss_recommend_topl_transfer(ctx.h, hY, hU, topl, 0, 4096, vi, vm))  # warm-up
+    ctx.sync()
+    e1.record(ext)
+    check(L.ss_recommend_topl_transfer(ctx.h, hY, hU, topl, 0, users, vi, vm))
+    e2.record(ext)
+    ctx.sync()
+    ms_stream = e1.elapsed_time(e2)
+    info = (ctypes.c_int64 * 4)()
+    check(L.ss_transfer_info(hU, info))
+    first = (idx[:users].clone(), val[:users].clone())
+    check(L.ss_recommend_topl_transfer(ctx.h, hY, hU, topl, 0, users, vi, vm))
+    ctx.sync()
+    identical = bool(torch.equal(first[0], idx[:users]) and torch.equal(first[1].view(torch.int64), val[:users].view(torch.int64)))
+    check(L.ss_transfer_destroy(hU))
+    pp = partial_products(G, users)
+    Ysp = sp.csr_matrix((np.ones(G["nnz"]), G["y_idx"].cpu().numpy(), G["y_ptr"].cpu().numpy()), shape=(ns, nt))
+    rows = np.sort(np.random.default_rng(5).choice(users, size=6, replace=False))
+    F, _ = o.two_layer_scores_sparse(Ysp, rows)
+    gi, gv = first[0].cpu().numpy(), first[1].cpu().numpy()
+    exact = True
+    for j, r in enumerate(rows):
+        dense = np.zeros(nt)
+        sl = slice(F.indptr[j], F.indptr[j + 1])
+        dense[F.indices[sl]] = F.data[sl]
+        order = o.sortperm_rev(dense)[:topl]
+        exact = exact and np.array_equal(gi[r], order) and np.array_equal(gv[r].view(np.uint64), dense[order].view(np.uint64))
+    out["C5_sparse_recommender_5pct_users"] = {
+        "users": ns, "items": nt, "edges": int(G["nnz"]), "L": topl, "users_ranked": users, "ms": ms_stream,
+        "partial_products": pp, "partial_products_per_s": pp / (ms_stream * 1e-3), "scores_per_s": users * nt / (ms_stream * 1e-3),
+        "algorithmic_gbs_10B_per_partial_product": pp * 10 / (ms_stream * 1e-3) / 1e9,
+        "transfer_matrix": {"entries": int(info[0]), "bytes": int(info[1]), "tile_width": int(info[2])},
+        "kernel": "tr_stream_kernel (shared-memory accumulators, no atomics) over the materialised transfer matrix",
+        "check": {"sampled_users": int(len(rows)), "top20_order_and_scores_bit_identical_to_scipy_sparse": bool(exact),
+                  "second_run_bit_identical": identical, "ok": bool(exact and identical)}}
+    return out
 
 
 def host_mem_available():
@@ -631,18 +850,23 @@ def host_mem_available():
     return 0
 
 
-def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq, bXs, bY, ldq, lds, ldy, sharded_step,
+def run_e2e(args, ss, ctx, torch, comm, np, dev, world, rank, d, nq_l, nt_l, bXq, bXs, bY, ldq, lds, ldy, sharded,
             mats):
-    """Same metric through the host-buffer entry point: pinned host inputs are copied to the device
-    and R is copied back inside the timed region, every step."""
+    """Same metric through the host-buffer entry points: pinned host inputs are copied to the device and R is copied
+    back inside the timed region, every step.  N = 1: ss_predict_query_host.  N > 1, per rank and per step: upload of
+    this rank's column shard of the replicated Xs (1/N of it; one NCCL all-gather over NVLink assembles Xs on every
+    GPU instead of N copies of the whole matrix over PCIe), upload of its Y block, the sharded front
+    (ss_sharded_front), and its query slab streamed through ss_stream_product_host (H2D / GEMM / D2H pipelined)."""
     from simspread_b200._lib import SS_PREDICT_CLEAN, check
     L = ss.lib()
     nq, ns, nf, nt = d["nq"], d["ns"], d["nf"], d["nt"]
     mXq, mXs, mY, mR, bR, ldr = mats
+    xs_cols = nf // world if nf % world == 0 else nf  # Xs shard of this rank (whole matrix if it does not divide)
+    xs_c0 = rank * xs_cols if xs_cols != nf else 0
     # host memory budget: shrink the query slab if the box cannot pin everything
-    fixed = (ns * nf + ns * nt_l) * 8
+    fixed = (ns * xs_cols + ns * nt_l) * 8
     per_q = (nf + nt) * 8
-    avail = host_mem_available()
+    avail = host_mem_available() // max(1, world)
     nq_e = nq_l
     if avail and fixed + nq_e * per_q > 0.6 * avail:
         nq_e = max(128, int((0.6 * avail - fixed) // per_q) // 128 * 128)
@@ -656,13 +880,13 @@ def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq
         return p, arr
 
     pXq, hXq = pinned(nq_e, nf)
-    pXs, hXs = pinned(ns, nf)
+    pXs, hXs = pinned(ns, xs_cols)
     pY, hY = pinned(ns, nt_l)
     pR, hR = pinned(nq_e, nt)
     # fill the host buffers with the device-resident operands (untimed)
     torch.cuda.synchronize()
     torch.from_numpy(hXq).copy_(bXq[:, :nq_e])
-    torch.from_numpy(hXs).copy_(bXs[:, :ns])
+    torch.from_numpy(hXs).copy_(bXs[xs_c0:xs_c0 + xs_cols, :ns])
     torch.from_numpy(hY).copy_(bY[:, :ns])
     torch.cuda.synchronize()
 
@@ -671,18 +895,20 @@ def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq
             check(L.ss_predict_query_host(ctx.h, pXq, nq_e, pXs, ns, pY, ns, nq_e, ns, nf, nt, SS_PREDICT_CLEAN,
                                           pR, nq_e))
     else:
-        be = sharded_step.b
+        hT, hkt = sharded.views()
 
         def e2e_step():
-            check(L.ss_mat_upload(ctx.h, mXs.h, pXs, ns))
+            check(L.ss_mat_upload_cols_async(ctx.h, mXs.h, xs_c0, xs_cols, pXs, ns))
+            if xs_cols != nf:
+                check(L.ss_comm_allgather_cols(comm.h, mXs.h))
             check(L.ss_mat_upload(ctx.h, mY.h, pY, ns))
-            sharded_step.front()  # degrees, spread, T block, fused all-gather of T
-            check(L.ss_stream_product_host(ctx.h, pXq, nq_e, nq_e, be.mT.h, be.vkt.h, pR, nq_e))
+            sharded.front(mXs, mY)  # degrees, two NCCL collectives, T tiles stored into every rank's T
+            check(L.ss_stream_product_host(ctx.h, pXq, nq_e, nq_e, hT, hkt, pR, nq_e))
 
     e2e_step()  # warm-up (allocates the streaming workspaces)
     ctx.sync()
     if world > 1:
-        dist.barrier()
+        comm.barrier()
     nsteps = max(1, min(args.steps, 2))
     # the call is synchronous and spans three streams (H2D / compute / D2H): the clock around the
     # synchronous call is the honest end-to-end time
@@ -693,18 +919,19 @@ def run_e2e(args, ss, ctx, torch, dist, np, dev, world, rank, d, nq_l, nt_l, bXq
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / nsteps
     if world > 1:
-        t_ = torch.tensor([wall], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        wall = float(t_.item())
+        wall = comm.allreduce_host([wall], "max")[0]
     got = torch.from_numpy(hR)[:64, :64]
-    same = bool(torch.equal(got.to(dev), bR[:64, :64])) if world == 1 and nq_e == nq_l else None
+    same = bool(torch.equal(got.to(dev), bR[:64, :64]))
+    if world > 1:
+        same = bool(comm.allreduce_host([0.0 if same else 1.0], "max")[0] == 0.0)
     res = {
         "value": (nq_e * world) * nt / wall, "unit": UNIT,
-        "h2d_bytes_per_step": int((nq_e * nf + ns * nf + ns * nt_l) * 8 * world),
+        "h2d_bytes_per_step": int((nq_e * nf + ns * xs_cols + ns * nt_l) * 8 * world),
         "d2h_bytes_per_step": int(nq_e * nt * 8 * world),
         "ms_per_step": wall * 1e3, "steps": nsteps, "queries": nq_e * world,
         "api": "ss_predict_query_host (pinned host buffers, slab-pipelined H2D / GEMM / D2H)" if world == 1 else
-               "per rank: ss_mat_upload(Xs, Y block) + sharded front (T over NVLink) + ss_stream_product_host",
+               "per rank: ss_mat_upload_cols_async(Xs shard) + ss_comm_allgather_cols (NVLink) + ss_mat_upload(Y block) + "
+               "ss_sharded_front (T over NVLink) + ss_stream_product_host",
         "matches_resident_run": same,
     }
     for p in (pXq, pXs, pY, pR):

@@ -75,6 +75,8 @@ typedef struct ss_mat ss_mat;   /* dense float64 column-major device matrix */
 typedef struct ss_ivec ss_ivec; /* int32 device vector (degrees, index lists) */
 typedef struct ss_csr ss_csr;   /* CSR device matrix (int32 row_ptr/col_idx, optional f64 values) */
 typedef struct ss_transfer ss_transfer; /* item x item block of W*W of a 2-layer graph, split by column tile */
+typedef struct ss_comm ss_comm;       /* one rank of a single-node NCCL communicator (one process per GPU) */
+typedef struct ss_sharded ss_sharded; /* state of the sharded predict: T (IPC-shared), degrees, peer mappings */
 
 /* ---- library / context ------------------------------------------------------------------- */
 SS_API int32_t ss_version(void);
@@ -266,6 +268,42 @@ SS_API int32_t ss_predict_query_host(ss_ctx* ctx, const double* Xq, int64_t ldxq
  * col_flag (optional), query-row slabs streamed H2D / GEMM / D2H on three streams. */
 SS_API int32_t ss_stream_product_host(ss_ctx* ctx, const double* Xq, int64_t ldxq, int64_t nq, const ss_mat* T,
                                       const ss_ivec* col_flag, double* R, int64_t ldr);
+
+/* ---- (3b) multi-GPU: the exchange steps of the sharded predict (SURVEY 8b `ss_comm_init`, 8e) ------------------
+ * One process per GPU of one node.  NCCL (dlopen of libnccl.so.2; override with SS_NCCL_LIBRARY) carries the
+ * all-reduce of the source degrees and the all-gather of the target degrees; the all-gather of the T tiles is fused
+ * into the T-GEMM epilogue over CUDA-IPC peer mappings (NVLink P2P stores), with an NCCL all-gather as the fallback
+ * (SS_FUSED_ALLGATHER=0 or no peer access).  The reference has no multi-GPU path: this is the north star's
+ * "sharded by query rows ... NCCL only to all-gather the target-side degree vector and W tiles".
+ * ss_comm_unique_id: 128 bytes created by ONE rank and passed to every rank through the host's own channel;
+ * ss_comm_init_file: the same through a file (rank 0 writes `path`, the others poll up to timeout_s; `path` must be
+ * unique to the job).  All calls are collective over the ranks of the communicator and synchronous on return. */
+SS_API int32_t ss_comm_unique_id(void* id128_out);
+SS_API int32_t ss_comm_init(ss_ctx* ctx, int32_t rank, int32_t world, const void* id128, ss_comm** out);
+SS_API int32_t ss_comm_init_file(ss_ctx* ctx, int32_t rank, int32_t world, const char* path, double timeout_s, ss_comm** out);
+SS_API int32_t ss_comm_destroy(ss_comm* comm);
+SS_API int32_t ss_comm_info(const ss_comm* comm, int32_t* rank, int32_t* world, int32_t* nccl_version);
+SS_API int32_t ss_comm_barrier(ss_comm* comm);
+SS_API int32_t ss_comm_allreduce_i32(ss_comm* comm, ss_ivec* v);                          /* in place, sum */
+SS_API int32_t ss_comm_allgather_i32(ss_comm* comm, const ss_ivec* send, ss_ivec* recv);  /* recv: world x send */
+SS_API int32_t ss_comm_allgather_host(ss_comm* comm, const void* send, void* recv, int64_t bytes); /* small host blobs */
+/* a replicated operand from sharded uploads: rank r filled column block r of M (cols divisible by world) */
+SS_API int32_t ss_comm_allgather_cols(ss_comm* comm, ss_mat* M);
+SS_API int32_t ss_comm_allreduce_host_f64(ss_comm* comm, double* x, int32_t n, int32_t op); /* op 0 = sum, 1 = max */
+/* Sharded predict for query rows: rank r owns Xq[r] / R[r] and the target-column block Y[:, r] (ns x nt_blk,
+ * nt_blk = ceil(nt / world), columns beyond nt zero); Xs (ns x nf) is replicated.  ss_sharded_create allocates T
+ * (nf x nt_blk*world per rank) and maps the peers' copies; ss_sharded_front = degrees -> all-reduce ks, all-gather kt
+ * -> Wst = Yblk ./ ks -> T[:, r] = (Xs' * Wst) ./ kf stored into every rank's T -> barrier; ss_predict_query_sharded
+ * = front + R slab = Xq slab * T with clean! fused (Xq / R may be NULL on a rank without query rows);
+ * ss_sharded_views: non-owning views of T (nf x nt) and kt (nt) for callers that stream their query rows
+ * (ss_stream_product_host). */
+SS_API int32_t ss_sharded_create(ss_comm* comm, int64_t ns, int64_t nf, int64_t nt, ss_sharded** out);
+SS_API int32_t ss_sharded_destroy(ss_sharded* plan);
+SS_API int32_t ss_sharded_info(const ss_sharded* plan, int64_t* nt_blk, int32_t* fused_allgather);
+SS_API int32_t ss_sharded_front(ss_sharded* plan, const ss_mat* Xs, const ss_mat* Yblk);
+SS_API int32_t ss_sharded_views(ss_sharded* plan, ss_mat** T, ss_ivec** kt);
+SS_API int32_t ss_predict_query_sharded(ss_sharded* plan, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Yblk, ss_mat* R,
+                                        uint32_t flags);
 
 /* ---- (4) ranking + metrics ----------------------------------------------------------------- */
 /* Per-row top-L of R under `sortperm(row; rev=true)` order [src/performance.jl:315,377]:

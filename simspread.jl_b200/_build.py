@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsimspread_b200.so"
-SOURCES = ["ss_api.cu", "ss_elementwise.cu", "ss_gemm.cu", "ss_csr.cu", "ss_rank.cu", "ss_sparse.cu", "ss_umma.cu", "ss_recsys.cu", "ss_transfer.cu", "ss_similarity.cu", "ss_io.cu"]
+SOURCES = ["ss_api.cu", "ss_elementwise.cu", "ss_gemm.cu", "ss_csr.cu", "ss_rank.cu", "ss_sparse.cu", "ss_umma.cu", "ss_recsys.cu", "ss_transfer.cu", "ss_comm.cu", "ss_similarity.cu", "ss_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     out = lib_path()
     if force or _stale(out, objs):
         cmd = [nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-Xcompiler", "-fPIC"]
+                                                      "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

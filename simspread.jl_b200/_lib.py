@@ -68,6 +68,23 @@ SIGNATURES = {
     "ss_csr_destroy": (c_i32, [vp]),
     "ss_csr_wrap": (c_i32, [vp, c_i64, c_i64, c_i64, vp, vp, vp, P(vp)]),
     "ss_recommend_topl": (c_i32, [vp, vp, vp, c_i32, c_i64, c_i64, vp, vp]),
+    "ss_comm_unique_id": (c_i32, [vp]),
+    "ss_comm_init": (c_i32, [vp, c_i32, c_i32, vp, P(vp)]),
+    "ss_comm_init_file": (c_i32, [vp, c_i32, c_i32, C.c_char_p, c_f64, P(vp)]),
+    "ss_comm_destroy": (c_i32, [vp]),
+    "ss_comm_info": (c_i32, [vp, P(c_i32), P(c_i32), P(c_i32)]),
+    "ss_comm_barrier": (c_i32, [vp]),
+    "ss_comm_allreduce_i32": (c_i32, [vp, vp]),
+    "ss_comm_allgather_i32": (c_i32, [vp, vp, vp]),
+    "ss_comm_allgather_host": (c_i32, [vp, vp, vp, c_i64]),
+    "ss_comm_allgather_cols": (c_i32, [vp, vp]),
+    "ss_comm_allreduce_host_f64": (c_i32, [vp, vp, c_i32, c_i32]),
+    "ss_sharded_create": (c_i32, [vp, c_i64, c_i64, c_i64, P(vp)]),
+    "ss_sharded_destroy": (c_i32, [vp]),
+    "ss_sharded_info": (c_i32, [vp, P(c_i64), P(c_i32)]),
+    "ss_sharded_front": (c_i32, [vp, vp, vp]),
+    "ss_sharded_views": (c_i32, [vp, P(vp), P(vp)]),
+    "ss_predict_query_sharded": (c_i32, [vp, vp, vp, vp, vp, c_u32]),
     "ss_transfer_build": (c_i32, [vp, vp, vp, P(vp)]),
     "ss_transfer_info": (c_i32, [vp, vp]),
     "ss_transfer_download": (c_i32, [vp, vp, vp, vp]),

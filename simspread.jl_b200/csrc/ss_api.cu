@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "ss_common.cuh"
 
@@ -105,6 +107,11 @@ int32_t ss_ctx_destroy(ss_ctx* ctx) {
     for (auto& s : ctx->ws)
         if (s.p) cudaFree(s.p);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->stage[i]) {
+            cudaFreeHost(ctx->stage[i]);
+            cudaEventDestroy(ctx->stage_ev[i]);
+        }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
@@ -261,11 +268,109 @@ static int32_t copy2d(ss_ctx* ctx, cudaStream_t st, void* dst, int64_t dpitch, c
     return SS_OK;
 }
 
+// ---- large copies from / to PAGEABLE host memory (what a NumPy / Julia array is) --------------------------------
+// cudaMemcpy on pageable memory stages through the driver's bounce buffer on one host thread (~10 GB/s).  Here the
+// columns go through three pinned staging buffers owned by the context: several host threads memcpy a chunk while the
+// DMA engine moves the previous one, which approaches the PCIe rate.  Pinned / registered memory takes the direct path.
+static bool host_is_pageable(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static void parallel_copy_cols(char* dst, size_t dpitch, const char* src, size_t spitch, size_t row_bytes, int64_t cols,
+                               int nthreads) {
+    auto work = [=](int64_t c0, int64_t c1) {
+        if (dpitch == row_bytes && spitch == row_bytes) {
+            memcpy(dst + size_t(c0) * dpitch, src + size_t(c0) * spitch, size_t(c1 - c0) * row_bytes);
+        } else {
+            for (int64_t c = c0; c < c1; ++c) memcpy(dst + size_t(c) * dpitch, src + size_t(c) * spitch, row_bytes);
+        }
+    };
+    if (nthreads <= 1 || cols < 2 * nthreads) {
+        work(0, cols);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t per = (cols + nthreads - 1) / nthreads;
+    for (int t = 1; t < nthreads; ++t) {
+        const int64_t c0 = std::min<int64_t>(cols, t * per), c1 = std::min<int64_t>(cols, c0 + per);
+        if (c0 < c1) th.emplace_back(work, c0, c1);
+    }
+    work(0, std::min<int64_t>(cols, per));
+    for (auto& x : th) x.join();
+}
+
+static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host, int64_t ldh, int64_t rows, int64_t cols,
+                             bool upload) {
+    constexpr size_t kStage = size_t(64) << 20;
+    constexpr int kBufs = 3;
+    const size_t row_bytes = size_t(rows) * 8;
+    if (row_bytes > kStage || rows == 0 || cols == 0) {  // a single column does not fit a staging buffer: direct copy
+        SS_TRY(copy2d(ctx, ctx->stream, upload ? (void*)dev : (void*)host, upload ? ldd : ldh, upload ? (const void*)host : (const void*)dev,
+                      upload ? ldh : ldd, rows, cols, upload ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SS_OK;
+    }
+    if (!ctx->stage[0]) {
+        for (int i = 0; i < kBufs; ++i) {
+            SS_CHECK_CUDA(cudaHostAlloc(&ctx->stage[i], kStage, cudaHostAllocDefault));
+            SS_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    const int nthreads = int(std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+    const int64_t cchunk = std::max<int64_t>(1, int64_t(kStage / row_bytes));
+    cudaStream_t st = upload ? ctx->copy_in : ctx->copy_out;
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));  // order against work already queued on the compute stream
+    if (upload) {
+        int b = 0;
+        for (int64_t c0 = 0; c0 < cols; c0 += cchunk, b = (b + 1) % kBufs) {
+            const int64_t nc = std::min(cchunk, cols - c0);
+            SS_CHECK_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));  // the DMA that last read this buffer is done
+            parallel_copy_cols(static_cast<char*>(ctx->stage[b]), row_bytes, reinterpret_cast<const char*>(host + c0 * ldh),
+                               size_t(ldh) * 8, row_bytes, nc, nthreads);
+            SS_CHECK_CUDA(cudaMemcpy2DAsync(dev + c0 * ldd, size_t(ldd) * 8, ctx->stage[b], row_bytes, row_bytes, size_t(nc),
+                                            cudaMemcpyHostToDevice, st));
+            SS_CHECK_CUDA(cudaEventRecord(ctx->stage_ev[b], st));
+        }
+        SS_CHECK_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // DMA of chunk i + 1 and i + 2 in flight while chunk i is copied out of its staging buffer
+        const int64_t nchunks = ceil_div(cols, cchunk);
+        auto issue = [&](int64_t i) -> cudaError_t {
+            const int b = int(i % kBufs);
+            const int64_t c0 = i * cchunk, nc = std::min(cchunk, cols - c0);
+            cudaError_t e = cudaMemcpy2DAsync(ctx->stage[b], row_bytes, dev + c0 * ldd, size_t(ldd) * 8, row_bytes, size_t(nc),
+                                              cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[b], st);
+            return e;
+        };
+        for (int64_t i = 0; i < std::min<int64_t>(kBufs - 1, nchunks); ++i) SS_CHECK_CUDA(issue(i));
+        for (int64_t i = 0; i < nchunks; ++i) {
+            const int b = int(i % kBufs);
+            const int64_t c0 = i * cchunk, nc = std::min(cchunk, cols - c0);
+            SS_CHECK_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
+            if (i + kBufs - 1 < nchunks) SS_CHECK_CUDA(issue(i + kBufs - 1));  // its buffer was emptied in the previous round
+            parallel_copy_cols(reinterpret_cast<char*>(host + c0 * ldh), size_t(ldh) * 8, static_cast<const char*>(ctx->stage[b]),
+                               row_bytes, row_bytes, nc, nthreads);
+        }
+        SS_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+    return SS_OK;
+}
+
+static constexpr int64_t kStagedCopyMinBytes = int64_t(32) << 20;
+
 int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host) {
     SS_ENTER(ctx);
     SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_upload: null argument");
     SS_REQUIRE(ld_host >= m->rows, "ss_mat_upload: ld_host (%lld) < rows (%lld)", (long long)ld_host,
                (long long)m->rows);
+    if (m->rows * m->cols * 8 >= kStagedCopyMinBytes && host_is_pageable(host))
+        return staged_copy2d(ctx, m->d, m->ld, const_cast<double*>(host), ld_host, m->rows, m->cols, true);
     SS_TRY(copy2d(ctx, ctx->stream, m->d, m->ld, host, ld_host, m->rows, m->cols, cudaMemcpyHostToDevice));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
@@ -276,6 +381,8 @@ int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_h
     SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_download: null argument");
     SS_REQUIRE(ld_host >= m->rows, "ss_mat_download: ld_host (%lld) < rows (%lld)", (long long)ld_host,
                (long long)m->rows);
+    if (m->rows * m->cols * 8 >= kStagedCopyMinBytes && host_is_pageable(host))
+        return staged_copy2d(ctx, m->d, m->ld, host, ld_host, m->rows, m->cols, false);
     SS_TRY(copy2d(ctx, ctx->stream, host, ld_host, m->d, m->ld, m->rows, m->cols, cudaMemcpyDeviceToHost));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;

@@ -61,6 +61,8 @@ struct ss_ctx {
     // workspaces reused across predict calls (never shrink)
     ss::Scratch ws[24];
     int32_t* tile_counter = nullptr;
+    void* stage[3] = {nullptr, nullptr, nullptr};  // pinned staging buffers of the pageable-memory copies
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     bool gemm_attr_set = false;
     // optional per-GEMM timing (ss_ctx_profile)
     bool profile = false;

@@ -371,6 +371,20 @@ class Graph:
                          DCsr.from_dense(self.ctx, self.Xs, ninf, True, by_columns=True))
         return self._csr
 
+    def density(self):
+        """(density of Xq, density of Xs) from the row-degree kernel (`ss_k_rows`, one pass over each block)."""
+        if getattr(self, "_density", None) is None:
+            out = []
+            for M in (self.Xq, self.Xs):
+                if M is None or M.rows * M.cols == 0:
+                    out.append(0.0)
+                    continue
+                kk = DIVec(self.ctx, M.rows)
+                check(lib().ss_k_rows(self.ctx.h, M.h, kk.h))
+                out.append(float(kk.to_host().sum(dtype=np.int64)) / float(M.rows * M.cols))
+            self._density = tuple(out)
+        return self._density
+
     def names(self, d: Optional[int] = None):
         n = [str(x) for x in self.queries + self.sources + self.features + self.targets]
         return [n, list(n)] if d is None else n
@@ -538,40 +552,64 @@ def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
     qpos = {n: i for i, n in enumerate(g.queries)}
     spos = {n: i for i, n in enumerate(g.sources)}
     tpos = {n: i for i, n in enumerate(g.targets)}
-    if not all(c in tpos for c in cols) or not all((r in qpos) or (r in spos) for r in rows):
-        # rows / columns outside the (query|source) x target block: literal dense path
+    in_block = all(c in tpos for c in cols) and all((r in qpos) or (r in spos) for r in rows)
+    want_q = any(r in qpos for r in rows) if in_block else False
+    # The block-reduced chain IS the reference's A * (W * W) only when W = spread(B) has no query
+    # edges (B masked, or a graph without queries), when the rows asked for exist in A (query rows of a masked A are
+    # zero) and when A and B are two views of the same construct() call.  Everything else -- predict(A, y) on the
+    # unmasked 4-layer graph (its feature degrees count the query edges too), predict((B, B), yq), graphs of two
+    # different construct() calls, names outside the (query | source) x target block -- takes the literal dense path.
+    same_blocks = A.Xs is B.Xs and A.Y is B.Y and A.Xq is B.Xq
+    block_ok = in_block and same_blocks and (B.masked or not g.queries) and not (A.masked and want_q)
+    if not block_ok:
         return _dense_predict(A.to_named(), B.to_named(), rows, cols)
     nt = len(g.targets)
-    out = np.empty((len(rows), len(cols)), order="F")
-    ci = [tpos[c] for c in cols]
-    want_q = [(i, qpos[r]) for i, r in enumerate(rows) if r in qpos]
-    want_s = [(i, spos[r]) for i, r in enumerate(rows) if r not in qpos]
-    if want_q:
-        if B is A and not B.masked:
-            # predict(A, y) with an unmasked 4-layer graph: W = spread(A) keeps the query rows;
-            # not the block-reduced form -- use the literal path
-            return _dense_predict(A.to_named(), A.to_named(), rows, cols)
+    ci = np.fromiter((tpos[c] for c in cols), dtype=np.int32, count=len(cols))
+    is_q = np.fromiter((r in qpos for r in rows), dtype=bool, count=len(rows))
+    ri = np.fromiter((qpos[r] if r in qpos else spos[r] for r in rows), dtype=np.int32, count=len(rows))
+    all_cols = len(cols) == nt and np.array_equal(ci, np.arange(nt, dtype=np.int32))
+
+    def fetch(R: DMat, row_sel: np.ndarray) -> np.ndarray:
+        """rows `row_sel`, columns `ci` of the device result as a host array: gathered on the device (one kernel), one
+        download -- no per-row host loop."""
+        if all_cols and len(row_sel) == R.rows and np.array_equal(row_sel, np.arange(R.rows, dtype=np.int32)):
+            return R.to_host()
+        sub = DMat(ctx, len(row_sel), len(ci))
+        check(lib().ss_gather(ctx.h, R.h, DIVec.from_host(ctx, row_sel).h, None if all_cols else DIVec.from_host(ctx, ci).h, sub.h))
+        return sub.to_host()
+
+    out = None
+    if is_q.any():
         R = DMat(ctx, len(g.queries), nt)
         if len(g.features) and len(g.sources):
             use_sparse = layout == "sparse"
-            if layout == "auto":
-                cq, cs = g.csr()
-                use_sparse = max(cq.density, cs.density) < SPARSE_DENSITY_THRESHOLD
+            if layout == "auto":  # density from the degree kernels (one pass), not from a CSR build
+                use_sparse = max(g.density()) < SPARSE_DENSITY_THRESHOLD
             if use_sparse:
                 cq, cs = g.csr()
                 check(lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, g.Y.h, R.h, flags, None))
             else:
                 check(lib().ss_predict_query(ctx.h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, None))
             g.last_layout = "sparse" if use_sparse else "dense"
-        Rh = R.to_host()
-        for i, qi in want_q:
-            out[i, :] = Rh[qi, ci]
-    if want_s:
+        else:  # no feature layer / no sources: the query rows of A * (W * W) are zero (ss_mat_create zero-fills)
+            if clean:
+                kt = DIVec(ctx, nt)
+                check(lib().ss_degrees(ctx.h, None, g.Y.h, None, None, kt.h))
+                check(lib().ss_clean(ctx.h, R.h, kt.h))
+        part = fetch(R, ri[is_q])
+        if is_q.all():
+            out = part
+        else:
+            out = np.empty((len(rows), len(cols)), order="F")
+            out[is_q, :] = part
+    if not is_q.all():
         R = DMat(ctx, len(g.sources), nt)
         check(lib().ss_predict_source(ctx.h, _h(g.Xs) if len(g.features) else None, g.Y.h, R.h, flags))
-        Rh = R.to_host()
-        for i, si in want_s:
-            out[i, :] = Rh[si, ci]
+        part = fetch(R, ri[~is_q])
+        if out is None:
+            out = part
+        else:
+            out[~is_q, :] = part
     return NamedArray(out, (rows, cols))
 
 

@@ -9,10 +9,11 @@ Sharding of R = Xq * T,  T = (Xs' * (Y ./ ks)) ./ kf:
     an int32 vector (rank 0 contributes the Xs term); kt[r] = nnz_col(Y[:, r]) -> all-gather
     (needed only by the fused clean!).
 
-`ShardedPredict.step()` is the choreography; the numerical work is delegated to a backend.  The
-product backend (`LibBackend`) calls libsimspread_b200 on device buffers owned by torch and uses
-torch.distributed (NCCL) for the three collectives.  tests/test_sharded_gloo.py drives the same
-choreography at world_size 2 on CPU with a NumPy test double and the gloo backend."""
+The product path is inside the library: `Comm` / `ShardedQuery` below are thin callers of `ss_comm_*`,
+`ss_sharded_*` and `ss_predict_query_sharded` (csrc/ss_comm.cu: NCCL + fused GEMM / all-gather over CUDA-IPC peer
+mappings).  `ShardedPredict` restates the same choreography step by step over a backend object; it exists so that the
+order of the exchange steps can be exercised on CPU: tests/test_sharded_gloo.py drives it at world_size 2 with a NumPy
+double and the gloo backend."""
 from __future__ import annotations
 
 import ctypes as C
@@ -91,130 +92,84 @@ class _CudaView:
                                          "version": 2}
 
 
-class LibBackend:
-    """Product backend: libsimspread_b200 kernels on torch-owned device buffers + NCCL."""
+class Comm:
+    """One rank of the library's NCCL communicator (`ss_comm`, include/simspread_b200.h section 3b).  The collectives
+    live behind the C ABI; this class only carries the unique id to the ranks: `exchange` is any callable that
+    returns rank 0's 128 bytes on every rank (e.g. a torch.distributed / MPI broadcast), or pass `path` for the
+    file rendezvous (`ss_comm_init_file`), which needs no other channel at all."""
 
-    def __init__(self, ss, ctx, torch, dist, plan: ShardPlan, ns: int, nf: int, bXq, ldq, bXs, lds, bY, ldy, bR, ldr):
-        from ._lib import check
-        self.ss, self.ctx, self.torch, self.dist, self.plan, self.check = ss, ctx, torch, dist, plan, check
-        self.L = ss.lib()
-        dev = bXs.device
-        p = plan
-        self.ns, self.nf = ns, nf
-        ld16 = lambda n: (n + 15) // 16 * 16
-        self.mXq = ss.DMat.wrap(ctx, bXq.data_ptr(), p.nq_local, nf, ldq)
-        self.mXs = ss.DMat.wrap(ctx, bXs.data_ptr(), ns, nf, lds)
-        self.mY = ss.DMat.wrap(ctx, bY.data_ptr(), ns, p.nt_blk, ldy)
-        self.mR = ss.DMat.wrap(ctx, bR.data_ptr(), p.nq_local, p.nt, ldr)
-        self.ldt = ld16(nf)
-        self.bW = torch.zeros((p.nt_blk, ld16(ns)), dtype=torch.float64, device=dev)
-        self.mW = ss.DMat.wrap(ctx, self.bW.data_ptr(), ns, p.nt_blk, ld16(ns))
-        self.tks = torch.zeros(ns, dtype=torch.int32, device=dev)
-        self.tkf = torch.zeros(nf, dtype=torch.int32, device=dev)
-        self.tkt = torch.zeros(p.nt_padded, dtype=torch.int32, device=dev)
-        self.tktl = torch.zeros(p.nt_blk, dtype=torch.int32, device=dev)
-        # T is library-owned (plain cudaMalloc) so that its IPC handle can be mapped by the peers;
-        # bT is a torch view of the same memory (checks, NCCL fallback).
-        self.mTfull = ss.DMat(ctx, nf, p.nt_padded, ipc=True)
-        _, _, ldt_, pT = self.mTfull.info()
-        assert ldt_ == self.ldt
-        self.bT = torch.as_tensor(_CudaView(pT, (p.nt_padded, self.ldt)), device=dev)
-        self.mT = ss.DMat.wrap(ctx, pT, nf, p.nt, self.ldt)
-        blk_off = p.rank * p.nt_blk * self.ldt * 8           # my column block inside any rank's T
-        self.mTl = ss.DMat.wrap(ctx, pT + blk_off, nf, p.nt_blk, self.ldt)
-        self.bTl = self.bT[p.rank * p.nt_blk:(p.rank + 1) * p.nt_blk]
-        self.mirrors = None
-        import os
-        if p.world > 1 and os.environ.get("SS_FUSED_ALLGATHER", "1") != "0":
-            self._open_peers(pT, blk_off)
-        self.vks, self.vkf = self._ivec(self.tks), self._ivec(self.tkf)
-        self.vktl = self._ivec(self.tktl)
-        self.vkt = self._ivec(self.tkt[:p.nt])
-
-    def _open_peers(self, pT, blk_off):
-        """Exchange CUDA IPC handles of T and map every peer's T: the T-GEMM epilogue then stores this
-        rank's column block straight into all peers (fused GEMM + all-gather over NVLink)."""
-        torch, dist, L = self.torch, self.dist, self.L
-        hbuf = (C.c_ubyte * 64)()
-        self.check(L.ss_mat_ipc_handle(self.ctx.h, self.mTfull.h, hbuf))
-        mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.bT.device)
-        allh = torch.zeros(64 * self.plan.world, dtype=torch.uint8, device=self.bT.device)
-        dist.all_gather_into_tensor(allh, mine)
-        allh = allh.cpu().numpy().reshape(self.plan.world, 64)
-        ptrs = []
-        try:
-            for r in range(self.plan.world):
-                if r == self.plan.rank:
-                    continue
-                raw = (C.c_ubyte * 64)(*allh[r].tolist())
-                dp = C.c_void_p()
-                self.check(L.ss_ipc_open(self.ctx.h, raw, C.byref(dp)))
-                ptrs.append(dp.value)
-        except Exception as e:  # no P2P / IPC on this box: keep the NCCL all-gather
-            print(f"[simspread_b200] rank {self.plan.rank}: peer mapping failed ({e}); using NCCL all-gather")
-            ptrs = None
-        ok = torch.tensor([1 if ptrs is not None else 0], device=self.bT.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 1:
-            self.peer_bases = ptrs
-            self.mirrors = (C.c_void_p * len(ptrs))(*[p_ + blk_off for p_ in ptrs])
-
-    def _ivec(self, t):
-        v = self.ss.DIVec.__new__(self.ss.DIVec)
-        v.ctx, v.n = self.ctx, t.numel()
+    def __init__(self, ctx, rank: int, world: int, exchange=None, path: str = None, timeout_s: float = 120.0):
+        from ._lib import check, lib
+        self.ctx, self.rank, self.world, self.L, self.check = ctx, int(rank), int(world), lib(), check
         h = C.c_void_p()
-        self.check(self.L.ss_ivec_wrap(self.ctx.h, C.c_void_p(t.data_ptr()), t.numel(), C.byref(h)))
-        v.h = h
-        return v
-
-    def _wait_collective(self):
-        self.torch.cuda.current_stream().synchronize()
-
-    def degrees(self, with_xs_rows: bool):
-        L, c = self.L, self.ctx.h
-        if with_xs_rows:
-            self.check(L.ss_degrees(c, self.mXs.h, self.mY.h, self.vks.h, self.vkf.h, self.vktl.h))
+        if path is not None:
+            check(self.L.ss_comm_init_file(ctx.h, self.rank, self.world, path.encode(), float(timeout_s), C.byref(h)))
         else:
-            self.check(L.ss_degrees(c, self.mXs.h, self.mY.h, None, self.vkf.h, self.vktl.h))
-            self.check(L.ss_k_rows(c, self.mY.h, self.vks.h))
-        if self.plan.world == 1:
-            self.tkt[:self.plan.nt_blk].copy_(self.tktl)
-            self._wait_collective()
+            buf = (C.c_ubyte * 128)()
+            if self.world > 1:
+                if self.rank == 0:
+                    check(self.L.ss_comm_unique_id(buf))
+                raw = exchange(bytes(buf))
+                assert len(raw) == 128
+                buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+            check(self.L.ss_comm_init(ctx.h, self.rank, self.world, buf, C.byref(h)))
+        self.h = h
 
-    def all_reduce_ks(self):
-        self.dist.all_reduce(self.tks)
-        self._wait_collective()
+    def barrier(self):
+        self.check(self.L.ss_comm_barrier(self.h))
 
-    def all_gather_kt(self):
-        self.dist.all_gather_into_tensor(self.tkt, self.tktl)
-        self._wait_collective()
+    def allreduce_host(self, values, op: str = "sum"):
+        """sum / max over the ranks of a short list of host doubles (timings, checksums)."""
+        arr = (C.c_double * len(values))(*[float(v) for v in values])
+        self.check(self.L.ss_comm_allreduce_host_f64(self.h, arr, len(values), 1 if op == "max" else 0))
+        return [float(x) for x in arr]
 
-    def spread(self):
-        self.check(self.L.ss_spread_rows(self.ctx.h, self.mY.h, self.vks.h, self.mW.h))
+    def nccl_version(self) -> int:
+        v = C.c_int32()
+        self.check(self.L.ss_comm_info(self.h, None, None, C.byref(v)))
+        return int(v.value)
 
-    def gemm_T(self):
-        from ._lib import SS_OP_T
-        if self.mirrors is not None:
-            self.check(self.L.ss_gemm_f64_mirrored(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h,
-                                                   None, len(self.mirrors), self.mirrors))
-        else:
-            self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_T, self.mXs.h, self.mW.h, self.mTl.h, self.vkf.h, None))
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ss_comm_destroy(self.h)
+            self.h = None
 
-    def all_gather_T(self):
-        if self.mirrors is not None:
-            # every rank's epilogue has already written its block into every T (the GEMM call
-            # returns after its stream has drained); a barrier orders those writes before the R GEMM
-            self.dist.barrier()
-        else:
-            self.dist.all_gather_into_tensor(self.bT.view(-1), self.bTl.reshape(-1).clone())
-        self._wait_collective()
+    __del__ = close
 
-    def gemm_R(self, clean: bool):
-        from ._lib import SS_OP_N
-        if self.plan.nq_local == 0:
-            return
-        self.check(self.L.ss_gemm_f64(self.ctx.h, SS_OP_N, self.mXq.h, self.mT.h, self.mR.h, None,
-                                      self.vkt.h if clean else None))
+
+class ShardedQuery:
+    """Thin caller of the sharded predict of the C ABI (`ss_sharded_*`, `ss_predict_query_sharded`): rank r passes its
+    query-row slab Xq[r] (nq_local x nf), the replicated Xs (ns x nf), its target-column block Y[:, r] (ns x nt_blk)
+    and receives R[r] (nq_local x nt).  Degrees, the two NCCL collectives and the T tiles stored into every rank's T
+    from the GEMM epilogue all happen inside the library."""
+
+    def __init__(self, comm: Comm, ns: int, nf: int, nt: int):
+        self.comm, self.L, self.check = comm, comm.L, comm.check
+        h = C.c_void_p()
+        self.check(self.L.ss_sharded_create(comm.h, int(ns), int(nf), int(nt), C.byref(h)))
+        self.h = h
+        blk, fused = C.c_int64(), C.c_int32()
+        self.check(self.L.ss_sharded_info(h, C.byref(blk), C.byref(fused)))
+        self.nt_blk, self.fused = int(blk.value), bool(fused.value)
+
+    def front(self, Xs, Yblk):
+        self.check(self.L.ss_sharded_front(self.h, Xs.h, Yblk.h))
+
+    def views(self):
+        """(T, kt) handles owned by the plan (non-owning for the caller)."""
+        t, k = C.c_void_p(), C.c_void_p()
+        self.check(self.L.ss_sharded_views(self.h, C.byref(t), C.byref(k)))
+        return t, k
+
+    def predict(self, Xq, Xs, Yblk, R, clean: bool = True):
+        from ._lib import SS_PREDICT_CLEAN
+        self.check(self.L.ss_predict_query_sharded(self.h, Xq.h if Xq is not None else None, Xs.h, Yblk.h,
+                                                   R.h if R is not None else None, SS_PREDICT_CLEAN if clean else 0))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ss_sharded_destroy(self.h)  # collective: closes the peer mappings after a barrier
+            self.h = None
 
 
 def combine_segment_summaries(sizes, summaries, rank: int):

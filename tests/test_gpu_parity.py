@@ -303,6 +303,45 @@ def test_predict_three_layer_and_two_layer(ss, o, iris):
         o.AuROC(Cc[[names.index(t) for t in q]].ravel() > 0, want.ravel()), rel=1e-12)
 
 
+def test_predict_forms_that_are_not_the_block_chain(ss, o, iris):
+    """predict() may use the block-reduced chain only where it IS the reference's A * (W * W) with W = spread(B):
+    (1) predict(A, y[sources]) on the UNMASKED 4-layer A: W = spread(A) counts the query edges in the feature
+    degrees; (2) predict((B, B), yq): the query rows of a masked A are zero; (3) graphs of two different construct()
+    calls; (4) query and source rows mixed in one call.  Each against the literal oracle (src/core.jl:402-466)."""
+    S, Cc, names, classes = iris["S"], iris["C"], iris["names"], iris["classes"]
+    X = ss.featurize(ss.NamedArray(S, (names, names)), 0.9, True)
+    y = ss.NamedArray(Cc, (names, classes))
+    q = names[::10]
+    tr = [n for n in names if n not in q]
+    A, B = ss.construct(y, X, q)
+    Xo, xr, xc = o.featurize(S, names, names, 0.9, True)
+    Ao, Bo, nn = o.construct_queries(Cc, (names, classes), Xo, (xr, xc), q)
+    some = tr[3:40:4]
+    # (1) W = spread(A), source rows and query rows
+    assert relerr(ss.predict(A, y[some, classes]).array, o.predict_dense(Ao, Ao, nn, some, classes)) < RTOL
+    assert relerr(ss.predict(A, y[q, classes]).array, o.predict_dense(Ao, Ao, nn, q, classes)) < RTOL
+    assert relerr(ss.predict((A, A), y[some, classes]).array, o.predict_dense(Ao, Ao, nn, some, classes)) < RTOL
+    # (2) A = B = masked graph: query rows are zero rows, source rows are the block form
+    got = ss.predict((B, B), y[q, classes]).array
+    assert np.array_equal(got, o.predict_dense(Bo, Bo, nn, q, classes)) and not got.any()
+    assert relerr(ss.predict((B, B), y[some, classes]).array, o.predict_dense(Bo, Bo, nn, some, classes)) < RTOL
+    # (3) A of one construct() call, B of another (other queries -> other feature / source sets of the same size)
+    q2 = names[5::10]
+    A2, B2 = ss.construct(y, X, q2)
+    A2o, B2o, nn2 = o.construct_queries(Cc, (names, classes), Xo, (xr, xc), q2)
+    rows3 = [n for n in q if n in nn2[:len(q2) + len(names) - len(q2)]][:5]
+    want3 = (A2o @ (o.spread(Bo) @ o.spread(Bo)))  # literal, by position: the node orders differ, as in the reference
+    got3 = ss.predict((A2, B), ss.NamedArray(np.zeros((len(rows3), len(classes))), (rows3, classes)))
+    ridx = [nn2.index(r) for r in rows3]
+    cidx = [nn2.index(c) for c in classes]
+    assert relerr(got3.array, want3[np.ix_(ridx, cidx)]) < RTOL
+    # (4) mixed query + source rows with the (A, B) pair: one call, two kernels, no per-row host loop
+    mixed = [q[0], some[0], q[3], some[2], some[1], q[1]]
+    assert relerr(ss.predict((A, B), y[mixed, classes]).array, o.predict_dense(Ao, Bo, nn, mixed, classes)) < RTOL
+    sub = classes[::-1][:2]
+    assert relerr(ss.predict((A, B), y[mixed, sub]).array, o.predict_dense(Ao, Bo, nn, mixed, sub)) < RTOL
+
+
 @pytest.mark.parametrize("nq,ns,nf,nt,slab", [(700, 300, 260, 190, 128), (33, 50, 40, 20, 16), (1, 3, 3, 2, 0)])
 def test_predict_query_host_pipelined(ss, o, nq, ns, nf, nt, slab):
     """The reference-facing host-buffer entry point (slabs of query rows streamed through)."""
@@ -431,30 +470,113 @@ def test_large_gemm_properties(ss):
     assert np.array_equal(dC.to_host(), A @ B)
 
 
-def test_sharded_backend_world1_matches_single_call(ss, o):
-    """The N > 1 product backend (LibBackend) on one GPU must reproduce ss_predict_query exactly."""
-    import torch
+def test_sharded_c_abi_world1_matches_single_call(ss, o):
+    """The N > 1 product path (ss_comm_* / ss_sharded_* / ss_predict_query_sharded behind the C ABI) with a
+    one-rank communicator must reproduce ss_predict_query bit for bit; the small collectives degrade to copies."""
     from simspread_b200._lib import SS_PREDICT_CLEAN, check
-    from simspread_b200.sharded import LibBackend, ShardedPredict, make_plan
+    from simspread_b200.sharded import Comm, ShardedQuery
     nq, ns, nf, nt = 200, 150, 130, 90
     Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=9, y_density=0.05, alpha=0.2, weighted=True)
     Y[:, 3] = 0.0
     ctx = ss.Context.default()
-    dev = torch.device("cuda", ctx.device)
+    L = ss.lib()
+    comm = Comm(ctx, 0, 1)
+    plan = ShardedQuery(comm, ns, nf, nt)
+    assert plan.nt_blk == nt and not plan.fused
+    dq, dx, dy = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y))
+    R1, R2 = ss.DMat(ctx, nq, nt), ss.DMat(ctx, nq, nt)
+    plan.predict(dq, dx, dy, R1, clean=True)
+    check(L.ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R2.h, SS_PREDICT_CLEAN, None))
+    got = R1.to_host()
+    assert np.array_equal(got, R2.to_host())
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    assert relerr(got, want) < RTOL
+    # a rank without query rows still takes part in the front; T / kt views feed the streaming product
+    plan.predict(None, dx, dy, None)
+    hT, hkt = plan.views()
+    Rh = np.zeros((nq, nt), order="F")
+    Xqf = np.asfortranarray(Xq)
+    check(L.ss_stream_product_host(ctx.h, Xqf.ctypes.data, nq, nq, hT, hkt, Rh.ctypes.data, nq))
+    assert np.array_equal(Rh, got)
+    # the helper collectives on one rank
+    v = ss.DIVec.from_host(ctx, np.arange(7, dtype=np.int32))
+    check(L.ss_comm_allreduce_i32(comm.h, v.h))
+    w = ss.DIVec(ctx, 7)
+    check(L.ss_comm_allgather_i32(comm.h, v.h, w.h))
+    assert np.array_equal(w.to_host(), np.arange(7))
+    assert comm.allreduce_host([1.5, -2.0], "max") == [1.5, -2.0]
+    check(L.ss_comm_allgather_cols(comm.h, dx.h))
+    comm.barrier()
+    plan.close()
+    comm.close()
 
-    def put(a):
-        ld = (a.shape[0] + 15) // 16 * 16
-        buf = torch.zeros((a.shape[1], ld), dtype=torch.float64, device=dev)
-        buf[:, :a.shape[0]] = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
-        return buf, ld
 
-    (bXq, ldq), (bXs, lds), (bY, ldy) = put(Xq), put(Xs), put(Y)
-    bR, ldr = put(np.zeros((nq, nt)))
-    torch.cuda.synchronize()
-    plan = make_plan(nq, nt, 1, 0)
-    be = LibBackend(ss, ctx, torch, None, plan, ns, nf, bXq, ldq, bXs, lds, bY, ldy, bR, ldr)
-    ShardedPredict(plan, be).step(clean=True)
-    got = bR[:, :nq].T.cpu().numpy()
+def _sharded_rank_main(rank, world, path, nq, ns, nf, nt, out_dir):
+    """One rank of the 2-GPU C-ABI test (spawned process): file rendezvous, sharded predict, result to disk."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import simspread_b200 as m
+    from oracle import simspread_oracle as oo
+    from simspread_b200.sharded import Comm, ShardedQuery
+    ctx = m.Context(rank)
+    Xq, Xs, Y = oo.synth_dense(nq, ns, nf, nt, seed=13, y_density=0.05, alpha=0.2, weighted=True)
+    Y[:, 5] = 0.0
+    comm = Comm(ctx, rank, world, path=path)
+    plan = ShardedQuery(comm, ns, nf, nt)
+    blk = plan.nt_blk
+    nq_blk = -(-nq // world)
+    q0, q1 = min(nq, rank * nq_blk), min(nq, (rank + 1) * nq_blk)
+    Yb = np.zeros((ns, blk))
+    c0, c1 = rank * blk, min(nt, (rank + 1) * blk)
+    Yb[:, :max(0, c1 - c0)] = Y[:, c0:c1]
+    dx, dy = m.DMat.from_host(ctx, Xs), m.DMat.from_host(ctx, Yb)
+    if q1 > q0:
+        dq, R = m.DMat.from_host(ctx, Xq[q0:q1]), m.DMat(ctx, q1 - q0, nt)
+        for _ in range(2):  # twice: the second front overwrites T while the peers may still hold the first
+            plan.predict(dq, dx, dy, R, clean=True)
+        res = R.to_host()
+    else:
+        for _ in range(2):
+            plan.predict(None, dx, dy, None)
+        res = np.zeros((0, nt))
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), res)
+    with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as f:
+        f.write(f"{int(plan.fused)} {comm.nccl_version()}")
+    plan.close()
+    comm.close()
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
+    """Two processes, two GPUs, nothing but the C ABI between them (NCCL dlopen()ed by the library, unique id through
+    a file, T tiles stored into the peer from the GEMM epilogue or all-gathered by NCCL): the row slabs must equal
+    the single-GPU result bit for bit (same kernels, same order of additions) and the oracle within 1e-12."""
+    import multiprocessing as mp
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    nq, ns, nf, nt = 301, 150, 130, 91  # ragged: the last rank owns fewer rows / target columns
+    os.environ["SS_FUSED_ALLGATHER"] = fused
+    try:
+        mpc = mp.get_context("spawn")
+        path = str(tmp_path / "nccl_id")
+        procs = [mpc.Process(target=_sharded_rank_main, args=(r, 2, path, nq, ns, nf, nt, str(tmp_path))) for r in range(2)]
+        for p_ in procs:
+            p_.start()
+        for p_ in procs:
+            p_.join(300)
+            assert p_.exitcode == 0
+    finally:
+        os.environ.pop("SS_FUSED_ALLGATHER", None)
+    got = np.concatenate([np.load(tmp_path / f"r{r}.npy") for r in range(2)])
+    flags = [open(tmp_path / f"r{r}.txt").read().split() for r in range(2)]
+    assert all(f[0] == fused for f in flags) or fused == "1"  # fused falls back to NCCL without peer access
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=13, y_density=0.05, alpha=0.2, weighted=True)
+    Y[:, 5] = 0.0
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    ctx = ss.Context.default()
     dq, dx, dy, R = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y, np.zeros((nq, nt))))
     check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
     assert np.array_equal(got, R.to_host())
