@@ -306,7 +306,7 @@ static void parallel_copy_cols(char* dst, size_t dpitch, const char* src, size_t
 
 static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host, int64_t ldh, int64_t rows, int64_t cols,
                              bool upload) {
-    constexpr size_t kStage = size_t(64) << 20;
+    constexpr size_t kStage = size_t(128) << 20;
     constexpr int kBufs = 3;
     const size_t row_bytes = size_t(rows) * 8;
     if (row_bytes > kStage || rows == 0 || cols == 0) {  // a single column does not fit a staging buffer: direct copy
@@ -321,7 +321,7 @@ static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host
             SS_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
         }
     }
-    const int nthreads = int(std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+    const int nthreads = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
     const int64_t cchunk = std::max<int64_t>(1, int64_t(kStage / row_bytes));
     cudaStream_t st = upload ? ctx->copy_in : ctx->copy_out;
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));  // order against work already queued on the compute stream
@@ -889,6 +889,19 @@ int32_t ss_predict_query_folds(ss_ctx* ctx, const ss_mat* X, const ss_mat* Y, in
     SS_CHECK_CUDA(cudaMemcpyAsync(dsx, s_idx + s_ptr[0], size_t(nsi) * 4, cudaMemcpyHostToDevice, ctx->stream));
     SS_CHECK_CUDA(cudaMemcpyAsync(dsy, ys_idx + s_ptr[0], size_t(nsi) * 4, cudaMemcpyHostToDevice, ctx->stream));
     SS_CHECK_CUDA(cudaMemcpyAsync(df, f_idx + f_ptr[0], size_t(nfi) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // Small folds (a cross-validation at Enzyme size): the fold is a grid dimension of three launches and the blocks
+    // are read through the index lists (ss_folds.cu).  Large folds keep the per-fold chain on the persistent DMMA GEMM.
+    {
+        bool small = prec == SS_PRECISION_F64 && std::max(ms, mf) <= 2048 && nt >= 1 && !getenv("SS_FOLDS_SERIAL");
+        for (int f = 0; small && f < nfolds; ++f)
+            small = q_ptr[f + 1] > q_ptr[f] && s_ptr[f + 1] > s_ptr[f] && f_ptr[f + 1] > f_ptr[f];
+        if (small) {
+            SS_TRY(predict_query_folds_batched(ctx, X, Y, nfolds, q_ptr, s_ptr, f_ptr, dq, dsx, dsy, df, R,
+                                               (flags & SS_PREDICT_CLEAN) != 0));
+            SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+            return SS_OK;
+        }
+    }
     // block buffers sized for the largest fold
     ss_mat bXq, bXs, bY, bR;
     bXq.ctx = bXs.ctx = bY.ctx = bR.ctx = ctx;

@@ -136,6 +136,9 @@ int32_t recommend_topl(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, in
                        int32_t* idx_out, double* val_out, int64_t ldv);
 int32_t recommend_topl_stream(ss_ctx* ctx, const ss_csr* Y, const ss_csr* YT, int L, int64_t s_begin, int64_t s_end,
                               int32_t* idx_out, double* val_out, int64_t ldv, bool* declined);
+int32_t predict_query_folds_batched(ss_ctx* ctx, const ss_mat* X, const ss_mat* Y, int nfolds, const int32_t* q_ptr,
+                                    const int32_t* s_ptr, const int32_t* f_ptr, const int32_t* dq, const int32_t* dsx,
+                                    const int32_t* dsy, const int32_t* df, ss_mat* R, bool clean);
 int32_t jaccard_featurize(ss_ctx* ctx, const ss_mat* A, const ss_mat* B, double alpha, bool weighted, ss_mat* X);
 int32_t tanimoto_bits_featurize(ss_ctx* ctx, const uint64_t* FA, int64_t na, const uint64_t* FB, int64_t nb, int64_t words,
                                 double alpha, bool weighted, ss_mat* X);

@@ -575,7 +575,9 @@ def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
         if all_cols and len(row_sel) == R.rows and np.array_equal(row_sel, np.arange(R.rows, dtype=np.int32)):
             return R.to_host()
         sub = DMat(ctx, len(row_sel), len(ci))
-        check(lib().ss_gather(ctx.h, R.h, DIVec.from_host(ctx, row_sel).h, None if all_cols else DIVec.from_host(ctx, ci).h, sub.h))
+        dri = DIVec.from_host(ctx, row_sel)            # keep the handles alive across the call
+        dci = None if all_cols else DIVec.from_host(ctx, ci)
+        check(lib().ss_gather(ctx.h, R.h, dri.h, _h(dci), sub.h))
         return sub.to_host()
 
     out = None

@@ -585,6 +585,42 @@ def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
     assert relerr(got, want) < RTOL
 
 
+@pytest.mark.parametrize("N,Nt,k_,weighted", [(445, 664, 10, False), (130, 70, 4, True), (67, 129, 67, True)])
+def test_folds_in_three_launches_match_the_per_fold_chain(ss, o, monkeypatch, N, Nt, k_, weighted):
+    """Small folds run as ONE grid over (fold, tile) -- degrees, T and R of every fold in three launches, operands read
+    through the fold index lists (ss_folds.cu).  Same predictions as the per-fold chain (gather, degrees, spread, two
+    DMMA GEMMs per fold) within the FP64 tolerance, same -99 flags, and both match the oracle loop."""
+    rng = np.random.default_rng(N + Nt)
+    S = np.round(rng.random((N, N)), 4)
+    Yf = (rng.random((N, Nt)) < 0.03).astype(float)
+    Yf[:, 2] = 0.0
+    names = [f"D{i:04d}" for i in range(N)]
+    tn = [f"T{j:04d}" for j in range(Nt)]
+    DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Yf, (names, tn))
+    ctx = ss.Context.default()
+    l0 = ctx.launch_count()
+    a = ss.cross_validate(DT, DD, 0.45, weighted=weighted, k_=k_, seed=3)
+    launches_batched = ctx.launch_count() - l0
+    monkeypatch.setenv("SS_FOLDS_SERIAL", "1")
+    l0 = ctx.launch_count()
+    b = ss.cross_validate(DT, DD, 0.45, weighted=weighted, k_=k_, seed=3)
+    launches_serial = ctx.launch_count() - l0
+    monkeypatch.delenv("SS_FOLDS_SERIAL")
+    assert a["folds"] == b["folds"]
+    assert relerr(a["yhat"].array, b["yhat"].array) < RTOL
+    assert np.array_equal(a["yhat"].array == -99, b["yhat"].array == -99)
+    assert launches_serial - launches_batched >= 5 * k_ - 3   # 7 launches per fold became 3 per CV
+    Xo, xr, xc = o.featurize(S, names, names, 0.45, weighted)
+    row = 0
+    for q in a["folds"]:
+        qi = [names.index(x) for x in q]
+        si = [i for i in range(N) if names[i] not in set(q)]
+        want = o.predict_blocks_query(Xo[np.ix_(qi, si)], Xo[np.ix_(si, si)], Yf[si])
+        o.clean_blocks(want, o.degrees_blocks(Xo[np.ix_(si, si)], Yf[si])[2])
+        assert relerr(a["yhat"].array[row:row + len(q)], want) < RTOL
+        row += len(q)
+
+
 def test_cross_validate_enzyme_shape_against_oracle_loop(ss, o):
     """BASELINE config 2: Enzyme-shaped (445 x 664), binary alpha-cutoff features, 10-fold CV."""
     S, Yfull = _enzyme_like(o, seed=20242)
