@@ -107,6 +107,32 @@ def test_c4_full_size_chain_properties(env):
     lhs = (kf_.to(torch.float64)[:, None] * Tc).sum(0)
     rhs = ((Xs.sum(0) * w)[:, None] * Y[cols].T).sum(0)
     assert relmax(torch, lhs, rhs) < 5e-12
+    # SURVEY 8(d) protocol for this size: >= 1e4 sampled entries recomputed on the HOST in extended precision (x87
+    # long double, 64-bit mantissa) from the reference's own formula -- W[f,s] = fl(Xs[s,f] / kf[f]),
+    # W[s,t] = fl(Y[s,t] / ks[s]) rounded to Float64 as `G ./ k(G)` does (src/core.jl:366), the sums of
+    # (W*W)[f,t] and of A * (W*W) exact to ~1e-19 -- against the FP64 result of the GPU at the north-star 1e-12.
+    ncol_s, nrow_s = 8, 1280
+    live = cols.cpu().numpy()
+    live = live[np.sort(np.unique(live, return_index=True)[1])][:ncol_s]
+    assert len(live) == ncol_s
+    rs = np.sort(np.random.default_rng(17).choice(nq, size=nrow_s, replace=False))
+    Xs_h = Xs.cpu().numpy()                                   # (nf, ns): row f = feature f over the sources
+    ks_h, kf_h = ks_.cpu().numpy(), kf_.cpu().numpy()
+    Y_h = Y[torch.from_numpy(live).to(dev)].cpu().numpy()     # (8, ns)
+    Xq_h = Xq[:, torch.from_numpy(rs).to(dev)].cpu().numpy()  # (nf, 1280)
+    got_h = R[torch.from_numpy(live).to(dev)][:, torch.from_numpy(rs).to(dev)].cpu().numpy()  # (8, 1280)
+    worst = 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for j in range(ncol_s):
+            src = np.flatnonzero(Y_h[j])
+            w_st = Y_h[j, src] / ks_h[src].astype(np.float64)                 # W[s,t], Float64 as in the reference
+            w_fs = np.where(kf_h[:, None] > 0, Xs_h[:, src] / kf_h[:, None].astype(np.float64), 0.0)  # W[f,s]
+            t_col = (w_fs.astype(np.longdouble) * w_st.astype(np.longdouble)[None, :]).sum(axis=1)     # (W*W)[f,t]
+            want_ld = (Xq_h.astype(np.longdouble) * t_col[:, None]).sum(axis=0)                          # F[q,t]
+            rel = np.abs(got_h[j].astype(np.longdouble) - want_ld) / np.maximum(np.abs(want_ld), np.longdouble(1e-300))
+            worst = max(worst, float(rel.max()))
+    assert ncol_s * nrow_s >= 10_000 and worst < RTOL, worst
+    del Xs_h, Xq_h
     # determinism / slab independence: the first 1000 query rows computed on their own are bit-identical
     bR2, ldr2 = colmajor(torch, 1000, nt, dev)
     mXq2 = ss.DMat.wrap(ctx, bXq.data_ptr(), 1000, nf, ldq)

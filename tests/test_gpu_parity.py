@@ -303,6 +303,59 @@ def test_predict_three_layer_and_two_layer(ss, o, iris):
         o.AuROC(Cc[[names.index(t) for t in q]].ravel() > 0, want.ravel()), rel=1e-12)
 
 
+def test_c4_replica_one_fiftieth_against_the_literal_path(ss, o):
+    """full comparison at a 1/50-scale replica of BASELINE config 4 (2 000 queries, 400 sources = 400
+    features, 1 000 targets; dense n = 3 800) against the LITERAL reference path -- construct the n x n matrices,
+    W = spread(B), F = A * (W * W), slice, clean! (src/core.jl:148-201, 365-371, 402-423, 478-484)."""
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    nq, ns, nf, nt = 2000, 400, 400, 1000
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=20244, y_density=0.05, alpha=0.0, weighted=True)
+    Y[:, 17] = 0.0
+    A = o._assemble4(Xq, Xs, Y)
+    B = A.copy()
+    B[:nq, :] = 0.0
+    B[:, :nq] = 0.0
+    names = [str(i) for i in range(nq + ns + nf + nt)]
+    rows, cols = names[:nq], names[nq + ns + nf:]
+    want = o.predict_dense(A, B, names, rows, cols)
+    o.clean(want, A, names, cols)
+    ctx = ss.Context.default()
+    dq, dx, dy, R = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y, np.zeros((nq, nt))))
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+    got = R.to_host()
+    assert relerr(got, want) < RTOL and np.array_equal(got == -99, want == -99) and (want[:, 17] == -99).all()
+    # the same through the host-buffer entry point (what the Julia `predict` wrapper ccalls)
+    Rh = np.zeros((nq, nt), order="F")
+    Xqf, Xsf, Yf = (np.asfortranarray(a) for a in (Xq, Xs, Y))
+    check(ss.lib().ss_predict_query_host(ctx.h, Xqf.ctypes.data, nq, Xsf.ctypes.data, ns, Yf.ctypes.data, ns, nq, ns, nf, nt,
+                                         SS_PREDICT_CLEAN, Rh.ctypes.data, nq))
+    assert np.array_equal(Rh, got)
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 0.95])
+def test_c3_full_size_against_block_oracle(ss, o, alpha):
+    """BASELINE config 3 at FULL size (5 000 queries, 5 000 sources = features, 2 000 targets, weighted) for three of
+    the 21 alpha points: dense end, middle, and the sparse end where predict(layout="auto") takes the row-split chain."""
+    nq = ns = 5000
+    nt = 2000
+    rng = np.random.default_rng(20243)
+    S = np.round(rng.random((nq + ns, ns)), 6)
+    Yall = (rng.random((nq + ns, nt)) < 0.01).astype(float)
+    X = o.cutoff(S, alpha, True)
+    Xq, Xs, Y = X[:nq], X[nq:], Yall[nq:]
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    qn, sn = [f"q{i}" for i in range(nq)], [f"s{i}" for i in range(ns)]
+    fn, tn = [f"f{i}" for i in range(ns)], [f"t{i}" for i in range(nt)]
+    G = ss.construct((ss.NamedArray(Y, (sn, tn)), ss.NamedArray(Yall[:nq], (qn, tn))),
+                     (ss.NamedArray(Xs, (sn, fn)), ss.NamedArray(Xq, (qn, fn))))
+    got = ss.predict(G, ss.NamedArray(Yall[:nq], (qn, tn)), clean=True)
+    assert G[0].last_layout == ("sparse" if alpha > 0.9 else "dense")
+    assert relerr(got.array, want) < RTOL and np.array_equal(got.array == -99, want == -99)
+    yb = Yall[:nq].ravel() > 0
+    assert ss.AuROC(yb, got.array.ravel()) == pytest.approx(o.AuROC(yb, want.ravel()), rel=1e-12)
+
+
 def test_predict_forms_that_are_not_the_block_chain(ss, o, iris):
     """predict() may use the block-reduced chain only where it IS the reference's A * (W * W) with W = spread(B):
     (1) predict(A, y[sources]) on the UNMASKED 4-layer A: W = spread(A) counts the query edges in the feature
