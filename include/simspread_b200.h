@@ -134,6 +134,17 @@ SS_API int32_t ss_ivec_download(ss_ctx* ctx, const ss_ivec* v, int32_t* host);
 SS_API int32_t ss_text_matrix_dims(const char* path, int32_t delimiter, int64_t* lines_out, int64_t* fields_out);
 SS_API int32_t ss_text_matrix_read(const char* path, int32_t delimiter, int32_t skip_lines, int32_t skip_fields,
                                    double* values, int64_t rows, int64_t cols, int64_t ld);
+/* `save(filepath, yhat, y; delimiter)` / `save(filepath, fidx, yhat, y; delimiter)` [src/core.jl:503-522, 542-561]:
+ * one line `fold <d> "query" <d> "target" <d> score <d> label` per pair, numbers as Julia's string(x) (shortest
+ * round-trip digits; an integer-typed matrix prints integers), byte-exact against test/data/save1..4.  fold < 0: the
+ * 1-based index of the query [src/core.jl:512].  yhat / y: host, column-major nq x nt in the row order of y; formatted
+ * by all host cores.  ss_save_rows_mat: the same from device-resident blocks (downloaded through pinned memory). */
+SS_API int32_t ss_save_rows(const char* path, int32_t append, int64_t fold, int64_t nq, int64_t nt, const char* const* qnames,
+                            const char* const* tnames, const double* yhat, int64_t ld_yhat, int32_t yhat_is_int,
+                            const double* y, int64_t ld_y, int32_t y_is_int, int32_t delimiter, int64_t* bytes_written);
+SS_API int32_t ss_save_rows_mat(ss_ctx* ctx, const char* path, int32_t append, int64_t fold, const char* const* qnames,
+                                const char* const* tnames, const ss_mat* yhat, const ss_mat* y, int32_t y_is_int,
+                                int32_t delimiter, int64_t* bytes_written);
 
 /* ---- (1) featurization ------------------------------------------------------------------- */
 /* cutoff.(S, alpha, weighted)  [src/core.jl:37-43 scalar rule, :55-60 array, :106-112 featurize,

@@ -58,6 +58,8 @@ SIGNATURES = {
     "ss_ivec_download": (c_i32, [vp, vp, vp]),
     "ss_text_matrix_dims": (c_i32, [C.c_char_p, c_i32, P(c_i64), P(c_i64)]),
     "ss_text_matrix_read": (c_i32, [C.c_char_p, c_i32, c_i32, c_i32, vp, c_i64, c_i64, c_i64]),
+    "ss_save_rows": (c_i32, [C.c_char_p, c_i32, c_i64, c_i64, c_i64, vp, vp, vp, c_i64, c_i32, vp, c_i64, c_i32, c_i32, P(c_i64)]),
+    "ss_save_rows_mat": (c_i32, [vp, C.c_char_p, c_i32, c_i64, vp, vp, vp, vp, c_i32, c_i32, P(c_i64)]),
     "ss_featurize": (c_i32, [vp, vp, c_f64, c_i32, vp]),
     "ss_featurize_csr": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),
     "ss_featurize_csc": (c_i32, [vp, vp, c_f64, c_i32, P(vp)]),

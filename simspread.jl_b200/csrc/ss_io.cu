@@ -9,7 +9,10 @@
 // trailing empty line is ignored.  Numbers go through std::from_chars (correctly rounded, like Julia's
 // parse(Float64, .)), plus the spellings Julia accepts that from_chars does not: a leading '+' and
 // surrounding blanks.
+#include <algorithm>
 #include <charconv>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -158,6 +161,175 @@ int32_t ss_text_matrix_read(const char* path, int32_t delimiter, int32_t skip_li
         SS_REQUIRE(bad[t] < 0, "ss_text_matrix_read: line %lld of %s does not hold %lld numeric fields",
                    (long long)(bad[t] + skip_lines + 1), path, (long long)cols);
     return SS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// `save` (reference src/core.jl:503-522, 542-561): one line `fold, "source", "target", score, label` per
+// (query, target) pair, appended to the file; numbers as Julia's `string(x)` prints them (shortest round-trip
+// digits, Base.Ryu.writeshortest: fixed notation for decimal exponents -4..5, `d.ddde-7` otherwise; an
+// integer-valued matrix prints integers).  All host cores format blocks of query rows; the blocks are written in order.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+inline void jl_append_float(std::string& out, double x) {
+    if (x != x) {
+        out += "NaN";
+        return;
+    }
+    if (x == 0.0) {
+        out += std::signbit(x) ? "-0.0" : "0.0";
+        return;
+    }
+    if (std::isinf(x)) {
+        out += x > 0 ? "Inf" : "-Inf";
+        return;
+    }
+    char buf[48];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);  // shortest: d[.ddd]e[+-]XX
+    const char* p = buf;
+    if (*p == '-') {
+        out += '-';
+        ++p;
+    }
+    char digits[24];
+    int nd = 0;
+    for (; p < r.ptr && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    ++p;  // 'e'
+    int e10 = 0;
+    bool eneg = false;
+    if (*p == '-') {
+        eneg = true;
+        ++p;
+    } else if (*p == '+') {
+        ++p;
+    }
+    for (; p < r.ptr; ++p) e10 = e10 * 10 + (*p - '0');
+    if (eneg) e10 = -e10;
+    while (nd > 1 && digits[nd - 1] == '0') --nd;
+    if (e10 > -5 && e10 < 6) {
+        if (e10 >= 0) {
+            for (int i = 0; i <= e10; ++i) out += i < nd ? digits[i] : '0';
+            out += '.';
+            if (nd > e10 + 1) out.append(digits + e10 + 1, size_t(nd - e10 - 1));
+            else out += '0';
+        } else {
+            out += "0.";
+            out.append(size_t(-e10 - 1), '0');
+            out.append(digits, size_t(nd));
+        }
+    } else {
+        out += digits[0];
+        out += '.';
+        if (nd > 1) out.append(digits + 1, size_t(nd - 1));
+        else out += '0';
+        out += 'e';
+        out += std::to_string(e10);
+    }
+}
+
+inline void jl_append_value(std::string& out, double x, bool as_int) {
+    if (as_int && x == double((long long)x)) out += std::to_string((long long)x);
+    else jl_append_float(out, x);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* yhat, y: host, column-major nq x nt (rows = the queries of y in its row order).  fold >= 0: that fold id on every
+ * line (src/core.jl:542-561); fold < 0: the 1-based index of the query (src/core.jl:512).  *_is_int: the matrix has
+ * an integer element type in the caller (prints `1`, not `1.0`). */
+int32_t ss_save_rows(const char* path, int32_t append, int64_t fold, int64_t nq, int64_t nt, const char* const* qnames,
+                     const char* const* tnames, const double* yhat, int64_t ld_yhat, int32_t yhat_is_int, const double* y,
+                     int64_t ld_y, int32_t y_is_int, int32_t delimiter, int64_t* bytes_written) {
+    SS_REQUIRE(path && nq >= 0 && nt >= 0 && (nq * nt == 0 || (qnames && tnames && yhat && y)), "ss_save_rows: null argument");
+    SS_REQUIRE(ld_yhat >= nq && ld_y >= nq, "ss_save_rows: leading dimension smaller than the number of queries");
+    FILE* f = fopen(path, append ? "a+" : "w");
+    SS_REQUIRE(f, "ss_save_rows: cannot open %s", path);
+    const char d = char(delimiter);
+    int64_t total = 0;
+    const int nthreads = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    // target-name fields are the same for every query: quote them once
+    std::vector<std::string> tq(static_cast<size_t>(nt));
+    for (int64_t t = 0; t < nt; ++t) tq[size_t(t)] = std::string("\"") + tnames[t] + "\"";
+    const int64_t rows_per_block = std::max<int64_t>(1, (int64_t(1) << 22) / std::max<int64_t>(nt, 1));  // ~4M lines per round
+    // two sets of per-thread buffers: the previous round is written by its own thread while this one is formatted
+    std::vector<std::string> sets[2] = {std::vector<std::string>(static_cast<size_t>(nthreads)),
+                                        std::vector<std::string>(static_cast<size_t>(nthreads))};
+    bool ok = true;
+    std::thread writer;
+    int cur = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += rows_per_block * nthreads, cur ^= 1) {
+        std::vector<std::string>& parts = sets[cur];
+        auto work = [&](int t) {
+            std::string& out = parts[size_t(t)];
+            out.clear();
+            const int64_t a = std::min(nq, q0 + int64_t(t) * rows_per_block), b = std::min(nq, a + rows_per_block);
+            for (int64_t q = a; q < b; ++q) {
+                const std::string head = std::to_string(fold >= 0 ? fold : q + 1) + d + "\"" + qnames[q] + "\"" + d;
+                for (int64_t c = 0; c < nt; ++c) {
+                    out += head;
+                    out += tq[size_t(c)];
+                    out += d;
+                    jl_append_value(out, yhat[c * ld_yhat + q], yhat_is_int != 0);
+                    out += d;
+                    jl_append_value(out, y[c * ld_y + q], y_is_int != 0);
+                    out += '\n';
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        if (writer.joinable()) writer.join();  // the other set is free again; rounds are written in order
+        writer = std::thread([&ok, &total, f, &parts]() {
+            for (const std::string& s : parts) {
+                if (ok && !s.empty()) ok = fwrite(s.data(), 1, s.size(), f) == s.size();
+                total += int64_t(s.size());
+            }
+        });
+    }
+    if (writer.joinable()) writer.join();
+    const bool closed = fclose(f) == 0;
+    SS_REQUIRE(ok && closed, "ss_save_rows: write to %s failed", path);
+    if (bytes_written) *bytes_written = total;
+    return SS_OK;
+}
+
+/* the same from device-resident score / label blocks (nq x nt): downloaded through pinned staging, then written */
+int32_t ss_save_rows_mat(ss_ctx* ctx, const char* path, int32_t append, int64_t fold, const char* const* qnames,
+                         const char* const* tnames, const ss_mat* yhat, const ss_mat* y, int32_t y_is_int, int32_t delimiter,
+                         int64_t* bytes_written) {
+    SS_REQUIRE(ctx && yhat && y && yhat->rows == y->rows && yhat->cols == y->cols, "ss_save_rows_mat: yhat and y must have the same shape");
+    SS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nq = yhat->rows, nt = yhat->cols;
+    double *hp = nullptr, *hy = nullptr;
+    const size_t bytes = size_t(std::max<int64_t>(nq * nt, 1)) * 8;
+    SS_CHECK_CUDA(cudaMallocHost(&hp, bytes));
+    if (cudaMallocHost(&hy, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeHost(hp);
+        ss::set_error("ss_save_rows_mat: out of pinned host memory");
+        return SS_ERR_OOM;
+    }
+    int32_t st = SS_OK;
+    if (nq * nt > 0) {
+        cudaError_t e = cudaMemcpy2DAsync(hp, size_t(nq) * 8, yhat->d, size_t(yhat->ld) * 8, size_t(nq) * 8, size_t(nt), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(hy, size_t(nq) * 8, y->d, size_t(y->ld) * 8, size_t(nq) * 8, size_t(nt), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            ss::set_error("ss_save_rows_mat: download failed: %s", cudaGetErrorString(e));
+            st = SS_ERR_CUDA;
+        }
+    }
+    if (st == SS_OK) st = ss_save_rows(path, append, fold, nq, nt, qnames, tnames, hp, nq, 0, hy, nq, y_is_int, delimiter, bytes_written);
+    cudaFreeHost(hp);
+    cudaFreeHost(hy);
+    return st;
 }
 
 }  // extern "C"

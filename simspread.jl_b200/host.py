@@ -1161,7 +1161,21 @@ def save(filepath: str, *args, delimiter: str = "\t") -> None:
     queries, targets = y.names(1), y.names(2)
     yh = yhat[queries, targets].array
     yy = y.array
-    with open(filepath, "a+") as f:
+    native = (len(delimiter) == 1 and ord(delimiter) < 128 and (fidx is None or isinstance(fidx, (int, np.integer)))
+              and all(a.dtype != np.bool_ and (np.issubdtype(a.dtype, np.floating) or np.issubdtype(a.dtype, np.integer)) for a in (yh, yy))
+              and len(set(queries)) == len(queries))
+    if native:
+        # the library formats and writes the rows with all host cores (ss_save_rows; Julia's number format in C++)
+        qn = (C.c_char_p * len(queries))(*[str(q).encode() for q in queries])
+        tn_ = (C.c_char_p * len(targets))(*[str(t).encode() for t in targets])
+        a_h, a_y = np.asfortranarray(yh, dtype=np.float64), np.asfortranarray(yy, dtype=np.float64)
+        nbytes = C.c_int64()
+        check(lib().ss_save_rows(os.fspath(filepath).encode(), 1, -1 if fidx is None else int(fidx), len(queries), len(targets),
+                                 qn, tn_, a_h.ctypes.data, max(1, a_h.shape[0]), int(np.issubdtype(yh.dtype, np.integer)),
+                                 a_y.ctypes.data, max(1, a_y.shape[0]), int(np.issubdtype(yy.dtype, np.integer)),
+                                 ord(delimiter), C.byref(nbytes)))
+        return
+    with open(filepath, "a+") as f:  # exotic element types / delimiters: the per-cell path
         for qi, q in enumerate(queries):
             fold = (queries.index(q) + 1) if fidx is None else fidx
             for ti, t in enumerate(targets):

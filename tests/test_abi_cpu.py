@@ -80,6 +80,47 @@ def test_host_bookkeeping_without_gpu():
     assert ss.mcc(0, 5, 0, 5) - ss.mcc(5, 5) < 1e-5
 
 
+def test_native_save_number_format_matches_julia_rules(tmp_path):
+    """ss_save_rows formats Float64 as Julia's string(x) (Base.Ryu.writeshortest: shortest round-trip digits, fixed
+    notation for decimal exponents -4..5, d.ddde-7 otherwise): compared with the host mirror's per-cell formatter on
+    awkward values, on random doubles of every magnitude, and on a block large enough to go through the threaded path."""
+    from simspread_b200.host import _jl_string
+    rng = np.random.default_rng(0)
+    special = [0.0, -0.0, 1.0, -1.0, 0.5, 0.1, 1 / 3, 2 / 3, 1e-5, 9.999e-5, 1e-4, 123456.0, 999999.9, 1e6, 1.5e6, 1e21, 1e22, 1e23,
+               5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, float("nan"), float("inf"), float("-inf"), -99.0,
+               0.30000000000000004, 100.0, 1e5, 12345.678, 7e-5, 6.02214076e23, 4.35e-6]
+    vals = np.array(special + list(rng.random(200)) + list(10.0 ** rng.uniform(-300, 300, 300) * rng.choice([-1, 1], 300)))
+    nq, nt = 4, len(vals) // 4
+    vals = vals[:nq * nt]
+    yhat = ss.NamedArray(np.asfortranarray(vals.reshape(nq, nt)), ([f"q{i}" for i in range(nq)], [f"t{j}" for j in range(nt)]))
+    y = ss.NamedArray((rng.random((nq, nt)) < 0.3).astype(np.int64), yhat.names())
+    p = tmp_path / "native.tsv"
+    ss.save(str(p), 7, yhat, y)
+    lines = p.read_text().splitlines()
+    assert len(lines) == nq * nt
+    k = 0
+    for qi in range(nq):
+        for ti in range(nt):
+            want = "\t".join(["7", f'"q{qi}"', f'"t{ti}"', _jl_string(float(yhat.array[qi, ti])), str(int(y.array[qi, ti]))])
+            assert lines[k] == want, (lines[k], want)
+            k += 1
+    for line, x in zip(lines, yhat.array.ravel(order="C")):
+        tok = line.split("\t")[3]
+        back = float(tok.replace("Inf", "inf").replace("NaN", "nan"))
+        assert back == x or (back != back and x != x)   # shortest digits round-trip
+    # a larger block: several threads, several rounds; fold column = 1-based query index
+    nq, nt = 700, 300
+    big = ss.NamedArray(np.round(rng.random((nq, nt)), 5), ([f"D{i}" for i in range(nq)], [f"T{j}" for j in range(nt)]))
+    lab = ss.NamedArray((rng.random((nq, nt)) < 0.1).astype(float), big.names())
+    p2 = tmp_path / "big.tsv"
+    ss.save(str(p2), big, lab, delimiter=" ")
+    rows = p2.read_text().splitlines()
+    assert len(rows) == nq * nt
+    for r in (0, 1, nt, 12345, nq * nt - 1):
+        qi, ti = divmod(r, nt)
+        assert rows[r] == " ".join([str(qi + 1), f'"D{qi}"', f'"T{ti}"', _jl_string(float(big.array[qi, ti])), _jl_string(float(lab.array[qi, ti]))])
+
+
 def test_save_matches_reference_fixtures(tmp_path, kats):
     """`save` is host-only I/O: byte-exact against test/data/save1..4 (test/runtests.jl:185-203)."""
     sv = kats["save"]
