@@ -282,3 +282,90 @@ def test_julia_ccalls_match_the_header():
             assert jl_class(t) == c_class(p), f"{name}: Julia type {t} against C parameter `{p}`"
         calls += 1
     assert calls >= 30
+
+
+# exported generics of the reference on the hot path (src/SimSpread.jl:21-56) with the signatures of src/core.jl,
+# src/performance.jl, src/graphs.jl, src/utils.jl: (name, positional parameters, of which optional, keyword names)
+_REFERENCE_API = [
+    ("split", 2, 0, {"seed"}),                                              # Base.split, src/core.jl:11
+    ("cutoff", 3, 1, set()), ("cutoff!", 3, 1, set()),                      # :37, :55, :72, :87
+    ("featurize", 3, 1, set()), ("featurize!", 3, 1, set()),                # :106, :129
+    ("construct", 3, 0, set()), ("construct", 2, 0, set()), ("construct", 4, 0, set()),   # :148, :217 / :308, :294
+    ("spread", 1, 0, set()),                                                # :365-380
+    ("predict", 2, 0, {"GPU"}), ("predict", 3, 0, {"GPU"}),                 # :402, :446, forwarder :424-425
+    ("clean!", 3, 0, set()),                                                # :478
+    ("save", 3, 0, {"delimiter"}), ("save", 4, 0, {"delimiter"}),           # :503, :542
+    ("BEDROC", 2, 0, {"rev", "α"}), ("AuROC", 2, 0, set()), ("AuPRC", 2, 0, set()),       # performance.jl:22, :49, :74
+    ("f1score", 4, 0, set()), ("mcc", 3, 1, set()), ("mcc", 4, 0, set()), ("accuracy", 4, 0, set()),
+    ("balancedaccuracy", 4, 0, set()), ("recall", 4, 0, set()), ("precision", 4, 0, set()),  # :102-296
+    ("recallatL", 3, 1, set()), ("recallatL", 4, 1, set()), ("precisionatL", 3, 1, set()), ("precisionatL", 4, 1, set()),
+    ("maxperformance", 3, 0, set()), ("meanperformance", 3, 0, set()), ("meanstdperformance", 3, 0, set()),
+    ("validity_ratio", 1, 0, set()),                                        # :558
+    ("k", 2, 0, set()), ("k", 1, 0, set()),                                 # graphs.jl:9-11
+    ("read_namedmatrix", 3, 2, {"rows", "cols"}),                           # utils.jl:50
+    ("writedlm", 2, 0, set()), ("writedlm", 3, 0, set()),                   # utils.jl:8-11
+]
+
+
+def _julia_definitions(src):
+    """(name, positional, optional, keyword names) of every `function name(...)` / `name(...) = ...` of the file."""
+    import re
+    defs = []
+    for m in re.finditer(r"^(?:function\s+)?((?:Base\.)?[A-Za-z_][\w!]*)\(", src, flags=re.M):
+        name = m.group(1).split(".")[-1]
+        i, depth = m.end(), 1
+        while depth and i < len(src):
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        args = src[m.end():i - 1]
+        rest = src[i:i + 200]
+        is_def = m.group(0).startswith("function") or re.match(r"\s*(where\s*\{[^}]*\}\s*)?=(?!=)", rest)
+        if not is_def:
+            continue
+        pos, _, kws = args.partition(";") if _top_level_semicolon(args) else (args, "", "")
+        plist = [a for a in _split_top_level(pos) if a.strip()]
+        klist = [a for a in _split_top_level(kws) if a.strip()]
+        opt = sum(1 for a in plist if re.search(r"(?<![=<>!])=(?!=)", _strip_braces(a)))
+        defs.append((name, len(plist), opt, {re.split(r"[:=]", a.strip())[0].strip().rstrip(".") for a in klist}))
+    return defs
+
+
+def _strip_braces(a):
+    out, depth = [], 0
+    for ch in a:
+        depth += {"{": 1, "}": -1, "(": 1, ")": -1, "[": 1, "]": -1}.get(ch, 0)
+        if depth == 0 and ch not in "})]":
+            out.append(ch)
+    return "".join(out)
+
+
+def _top_level_semicolon(args):
+    depth = 0
+    for ch in args:
+        depth += {"(": 1, ")": -1, "{": 1, "}": -1, "[": 1, "]": -1}.get(ch, 0)
+        if ch == ";" and depth == 0:
+            return True
+    return False
+
+
+def test_julia_layer_defines_the_reference_api():
+    """Table-driven: every exported generic of the reference on the hot path is defined in SimSpreadB200.jl with the
+    same number of positional parameters, the same optional ones, and (at least) the same keyword names."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "simspread.jl_b200", "julia", "SimSpreadB200.jl")).read()
+    defs = _julia_definitions(jl)
+    exported = set(re_findall_exports(jl))
+    missing = []
+    for name, npos, nopt, kws in _REFERENCE_API:
+        ok = any(d[0] == name and d[1] == npos and d[2] >= nopt and kws <= d[3] for d in defs)
+        if not ok:
+            missing.append((name, npos, nopt, sorted(kws), [d for d in defs if d[0] == name]))
+        if name != "split":
+            assert name in exported, f"{name} is not exported"
+    assert not missing, missing
+
+
+def re_findall_exports(jl):
+    import re
+    m = re.search(r"^export (.*?)\n\n", jl, flags=re.S | re.M)
+    return [x.strip() for x in m.group(1).replace("\n", " ").split(",") if x.strip()]
