@@ -254,3 +254,34 @@ def test_auroc_auprc_restatement_against_scikit_learn_counts():
         assert o.AuPRC(y, s) == pytest.approx(abs(trapezoid(prec[:-1], rec[:-1])), rel=1e-12)
     # the documented consequence of the missing anchors: 2/3 instead of the textbook 0.75
     assert o.AuROC(np.array([1, 0, 1, 0, 0], bool), np.array([.9, .9, .7, .1, .1])) == pytest.approx(2 / 3, rel=1e-12)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_two_layer_ordered_oracle_pins_scipy(weighted):
+    """The oracle of the sparse recommender form (BASELINE config 5) is the reference's association A * (W * W)
+    (src/core.jl:456) with every sum in ascending index order.  Its fast form uses scipy.sparse CSR x CSR products; this
+    pins that they add in exactly that order (bit-equal to literal Python loops) and that the result agrees with the
+    dense block form and the literal n x n path within the FP64 tolerance -- but NOT bit for bit (BLAS order), which is
+    why the bit-exact top-L tests need the ordered form."""
+    rng = np.random.default_rng(4 + int(weighted))
+    mask = rng.random((60, 45)) < 0.15
+    Y = np.where(mask, np.round(rng.random((60, 45)) + 0.5, 3), 0.0) if weighted else mask.astype(float)
+    Y[7, :] = 0.0
+    Y[:, 3] = 0.0
+    F_loops = o.two_layer_scores_loops(Y)
+    F_sp, U_sp = o.two_layer_scores_sparse(Y)
+    assert np.array_equal(F_sp.toarray(), F_loops)
+    assert np.array_equal(U_sp.toarray(), o.two_layer_transfer_loops(Y))
+    F_rows, _ = o.two_layer_scores_sparse(Y, rows=[5, 7, 41])
+    assert np.array_equal(F_rows.toarray(), F_loops[[5, 7, 41]])
+    n = 60 + 45
+    A = np.zeros((n, n))
+    A[:60, 60:] = Y
+    A[60:, :60] = Y.T
+    names = [f"n{i}" for i in range(n)]
+    lit = o.predict_dense_single(A, names, names[:60], names[60:])
+    nz = lit != 0
+    assert np.max(np.abs(F_loops[nz] - lit[nz]) / lit[nz]) < 1e-13 and not F_loops[~nz].any()
+    idx, val = o.recommend_topl(Y, 5)
+    assert np.array_equal(idx[0], o.sortperm_rev(F_loops[0])[:5]) and np.array_equal(val[0], F_loops[0][idx[0]])
+    assert np.array_equal(idx[7], np.arange(5))   # a source without items: all scores 0 -> the first columns
