@@ -730,13 +730,15 @@ def run_side_configs(ss, np, torch, ctx, dev):
     S, Y, names, tn, folds, alpha, weighted = synth_small_config(np, "C2")
     DD, DT = ss.NamedArray(S, (names, names)), ss.NamedArray(Y, (names, tn))
     ss.cross_validate(DT, DD, alpha, weighted=weighted, folds=folds)
-    ts, launches = [], 0
+    ts, launches, tf = [], 0, []
     for _ in range(5):
         l0 = ctx.launch_count()
+        tm = {}
         t0 = time.perf_counter()
-        res = ss.cross_validate(DT, DD, alpha, weighted=weighted, folds=folds)
+        res = ss.cross_validate(DT, DD, alpha, weighted=weighted, folds=folds, timing=tm)
         ts.append(time.perf_counter() - t0)
         launches = ctx.launch_count() - l0
+        tf.append(tm)
     Xo, xr, xc = o.featurize(S, names, names, alpha, weighted)
     worst, row = 0.0, 0
     for q in folds:
@@ -756,6 +758,8 @@ def run_side_configs(ss, np, torch, ctx, dev):
     out["C2_enzyme_10fold_cv"] = {
         "shape": [len(names), len(tn)], "alpha": alpha, "weighted": weighted, "ms_per_cv_wall_median_of_5": float(np.median(ts)) * 1e3,
         "scores_per_s": len(names) * len(tn) / float(np.median(ts)), "kernel_launches_per_cv": int(launches),
+        "folds_call_ms_median": float(np.median([t_["folds_call_ms"] for t_ in tf])),
+        "folds_call_kernel_launches": int(tf[-1]["folds_call_launches"]),
         "includes": "upload, featurize, 10 folds (gather, degrees, spread, T, R + clean!), AuROC/AuPRC, @20 metrics, download",
         "check": {"max_rel_err_vs_oracle_block_form": worst, "tolerance": 1e-12,
                   "AuROC_rel_diff_vs_oracle": abs(res["AuROC"] - o.AuROC(yb, res["yhat"].array.ravel())) / max(res["AuROC"], 1e-300),

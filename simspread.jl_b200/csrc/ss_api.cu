@@ -196,7 +196,9 @@ static int32_t mat_create(ss_ctx* ctx, int64_t rows, int64_t cols, ss_mat** out,
     m->ctx = ctx;
     m->rows = rows;
     m->cols = cols;
-    m->ld = round_up(rows > 0 ? rows : 1, 16);
+    // columns start on 128-byte boundaries (TMA, 128-bit loads); a skinny matrix (a vector uploaded as 1 x n for the
+    // ungrouped @L metrics or k(vector)) keeps 16-byte column alignment only: padding 1 row to 16 is a 16 x blow-up
+    m->ld = rows >= 16 ? round_up(rows, 16) : round_up(rows > 0 ? rows : 1, 2);
     m->owned = true;
     const size_t bytes = size_t(m->ld) * size_t(cols > 0 ? cols : 1) * 8 + 256;
     // stream-ordered pool allocation: no device-wide synchronisation per matrix (CV loops create
@@ -698,8 +700,16 @@ static int32_t chain_gemm(ss_ctx* ctx, uint32_t precision, int opA, const double
         const char* ce = getenv("SS_INT8_CERTIFY");
         const bool certify = !(ce && ce[0] == '0');
         int64_t bad = 0;
-        SS_TRY(launch_gemm_i8(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, S, certify ? tol : 0.0,
-                              certify ? &bad : nullptr));
+        const int32_t st8 = launch_gemm_i8(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, S, certify ? tol : 0.0,
+                                           certify ? &bad : nullptr);
+        if (st8 == SS_ERR_INVALID) {
+            // a shape the sliced mode cannot take (K too long for exact INT32 accumulation): the documented behaviour of
+            // this mode is the FP64 DMMA path, counted as a re-run.  (Negative / non-finite operands stay an error:
+            // SS_ERR_UNSUPPORTED, the caller asked for a mode that is not defined for them.)
+            ctx->int8_stats[1] += 1;
+            return launch_gemm_f64(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, false);
+        }
+        SS_TRY(st8);
         ctx->int8_stats[0] += 1;
         ctx->int8_stats[2] = bad;
         if (bad > 0) {

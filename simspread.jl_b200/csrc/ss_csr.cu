@@ -8,7 +8,12 @@
 // columns in tiles of 64: the tile is loaded with lanes along rows (256-byte coalesced runs of one
 // column), transposed through padded shared memory, and compacted with lanes along columns:
 // __ballot_sync + popc prefix give every kept entry its slot, so the col_idx / value stores of one
-// row are contiguous.  The same kernel run in COUNT mode produces the row counts for the scan.
+// row are contiguous.  The same kernel run in COUNT mode produces the row counts for the scan -- and the keep-mask
+// (one bit per cell), which the fill pass of a SPARSE result replays instead of reading S a second time
+// (csr_fill_mask_kernel): S is then read once, plus the sectors of the kept entries.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ss_common.cuh"
 
 namespace {
@@ -26,7 +31,7 @@ template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(CSR_TPB)
     csr_kernel(const double* __restrict__ S, int64_t rows, int64_t cols, int64_t ld, double alpha, int weighted,
                int32_t* __restrict__ row_count, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx,
-               double* __restrict__ values) {
+               double* __restrict__ values, uint32_t* __restrict__ keep_mask, int64_t mask_words) {
     __shared__ double tile[TILE_COLS][ROWS_PER_BLOCK + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = int64_t(blockIdx.x) * ROWS_PER_BLOCK;
@@ -55,6 +60,8 @@ __global__ void __launch_bounds__(CSR_TPB)
                 const double x = tile[32 * h + lane][rr];
                 const bool keep = keep_edge(x, alpha, w);
                 const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                if (COUNT_ONLY && keep_mask && lane == 0 && row0 + rr < rows && c0 + 32 * h < cols)
+                    keep_mask[(row0 + rr) * mask_words + (c0 >> 5) + h] = ballot;  // replayed by csr_fill_mask_kernel
                 if (!COUNT_ONLY && keep) {
                     const int32_t pos = cursor[q] + __popc(ballot & ((1u << lane) - 1u));
                     col_idx[pos] = int32_t(c0 + 32 * h + lane);
@@ -71,6 +78,42 @@ __global__ void __launch_bounds__(CSR_TPB)
             const int64_t r = row0 + 4 * warp + q;
             if (r < rows) row_count[r] = cursor[q];
         }
+    }
+}
+
+// Fill pass for sparse results: instead of reading S a second time, replay the keep-mask written by the count pass
+// (1/64 of the bytes of S) and touch only the sectors of the kept entries.  One warp per row; lane l takes mask word
+// l, l + 32, ...; a warp prefix over the popcounts gives every kept entry its slot, so col_idx / values of a row are
+// written in ascending column order, bit-identical to the tiled fill.
+__global__ void __launch_bounds__(256)
+    csr_fill_mask_kernel(const double* __restrict__ S, int64_t rows, int64_t ld, const uint32_t* __restrict__ keep_mask,
+                         int64_t mask_words, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx,
+                         double* __restrict__ values) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const uint32_t* m = keep_mask + row * mask_words;
+    int32_t base = row_ptr[row];
+    for (int64_t w0 = 0; w0 < mask_words; w0 += 32) {
+        const int64_t w = w0 + lane;
+        uint32_t bits = w < mask_words ? __ldg(m + w) : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        int32_t pos = base + incl - cnt;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int64_t c = (w << 5) + b;
+            col_idx[pos] = int32_t(c);
+            if (values) values[pos] = __ldg(S + c * ld + row);  // weighted: the kept value is the similarity itself
+            ++pos;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -131,9 +174,20 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
     int32_t* counts = static_cast<int32_t*>(p);
     int32_t* overflow = counts + rows + 1;
     const unsigned grid = unsigned(ceil_div(rows > 0 ? rows : 1, ROWS_PER_BLOCK));
+    // keep-mask of the count pass (one bit per cell): lets the fill pass of a sparse result skip the second read of S
+    const int64_t mask_words = ceil_div(cols, 32);
+    uint32_t* keep_mask = nullptr;
+    {
+        const char* e = getenv("SS_CSR_FILL");  // "tiled": always re-read S through the transposing tiles (A/B runs)
+        if (!(e && !strcmp(e, "tiled")) && rows > 0 && cols > 0) {
+            void* mp;
+            if ((status = scratch_get(ctx, 22, size_t(rows) * size_t(mask_words) * 4, &mp)) != SS_OK) return fail(status);
+            keep_mask = static_cast<uint32_t*>(mp);
+        }
+    }
     if (rows > 0 && cols > 0) {
         csr_kernel<true><<<grid, CSR_TPB, 0, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0, counts,
-                                                             nullptr, nullptr, nullptr);
+                                                             nullptr, nullptr, nullptr, keep_mask, mask_words);
         ctx->launches++;
     } else {
         cudaMemsetAsync(counts, 0, size_t(rows + 1) * 4, ctx->stream);
@@ -161,8 +215,16 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
         return fail(SS_ERR_OOM);
     }
     if (c->nnz > 0) {
-        csr_kernel<false><<<grid, CSR_TPB, 0, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0, nullptr,
-                                                              c->row_ptr, c->col_idx, c->values);
+        // below ~10 % density the mask replay moves fewer bytes than a second sweep of S (a kept value costs one
+        // 32-byte sector); above it the transposing tiles are the better access pattern
+        const bool replay = keep_mask && double(c->nnz) < 0.10 * double(rows) * double(cols);
+        if (replay) {
+            csr_fill_mask_kernel<<<unsigned(ceil_div(rows * 32, 256)), 256, 0, ctx->stream>>>(S->d, rows, S->ld, keep_mask, mask_words,
+                                                                                          c->row_ptr, c->col_idx, c->values);
+        } else {
+            csr_kernel<false><<<grid, CSR_TPB, 0, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0, nullptr,
+                                                                  c->row_ptr, c->col_idx, c->values, nullptr, 0);
+        }
         ctx->launches++;
     }
     e = cudaGetLastError();

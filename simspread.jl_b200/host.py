@@ -80,9 +80,13 @@ class Context:
         return [(ms[i], fl[i]) for i in range(n.value)]
 
     def close(self):
+        """Destroys the context.  Handles created on it (DMat / DIVec / DCsr) notice (`ctx.h is None`) and skip their
+        own destroy call instead of handing the library a dangling context."""
         if self.h:
             lib().ss_ctx_destroy(self.h)
             self.h = None
+            if Context._default is self:
+                Context._default = None
 
 
 def _f64_colmajor(a) -> np.ndarray:
@@ -133,9 +137,9 @@ class DMat:
 
     def __del__(self):
         try:
-            if getattr(self, "h", None):
+            if getattr(self, "h", None) and getattr(self.ctx, "h", None):  # a closed context took its memory with it
                 lib().ss_mat_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -165,9 +169,9 @@ class DIVec:
 
     def __del__(self):
         try:
-            if getattr(self, "h", None):
+            if getattr(self, "h", None) and getattr(self.ctx, "h", None):
                 lib().ss_ivec_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -204,9 +208,9 @@ class DCsr:
 
     def __del__(self):
         try:
-            if getattr(self, "h", None):
+            if getattr(self, "h", None) and getattr(self.ctx, "h", None):
                 lib().ss_csr_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -857,7 +861,7 @@ class _FoldIndexer:
 
 def cross_validate(DT: NamedArray, DD: NamedArray, alpha: float, weighted: bool = True, k_: int = 10,
                    seed: int = 1, L: int = 20, folds: Optional[List[List[str]]] = None, rank: int = 0,
-                   world: int = 1) -> dict:
+                   world: int = 1, timing: Optional[dict] = None) -> dict:
     """k-fold de-novo cross-validation: `split` -> `featurize` -> per fold `construct`, `predict`,
     `clean!` -> AuROC / AuPRC over all (query, target) pairs and mean recall@L / precision@L per
     query.  Returns the predictions with rows in fold order.
@@ -898,9 +902,14 @@ def cross_validate(DT: NamedArray, DD: NamedArray, alpha: float, weighted: bool 
     qa, sa, ysa, fa = _i32(q_all), _i32(s_all), _i32(ys_all), _i32(f_all)
     qp, sp, fp = (np.asarray(v, dtype=np.int32) for v in (q_ptr, s_ptr, f_ptr))
     if len(order):
+        import time as _time
+        l0, t0 = ctx.launch_count(), _time.perf_counter()
         check(lib().ss_predict_query_folds(ctx.h, dX.h, dy.h, len(folds), qp.ctypes.data, qa.ctypes.data, sp.ctypes.data,
                                            sa.ctypes.data, ysa.ctypes.data, fp.ctypes.data, fa.ctypes.data, Rall.h,
                                            SS_PREDICT_CLEAN))
+        if timing is not None:  # the call is synchronous: index upload + every fold's degrees / T / R + clean!
+            timing["folds_call_ms"] = (_time.perf_counter() - t0) * 1e3
+            timing["folds_call_launches"] = ctx.launch_count() - l0
     perm = DIVec.from_host(ctx, DT.index_of(order, 1))
     Yall = DMat(ctx, len(order), nt)
     check(lib().ss_gather(ctx.h, dy.h, perm.h, None, Yall.h))

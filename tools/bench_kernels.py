@@ -79,9 +79,17 @@ def csr(alpha, weighted):
     return nnz.value
 
 
-nnz = csr(0.9, 1)
-report("featurize_csr (count + scan + fill, weighted, alpha=0.9)", n, "elements", 16 * n + 12 * nnz + 4 * rows,
-       lambda: csr(0.9, 1), f"2 x 8 B read per element + 12 B per kept edge ({nnz} edges); includes cudaMalloc of the CSR")
+nnz = csr(0.96, 1)
+report("featurize_csr (count + mask, scan, mask-replay fill; weighted, alpha=0.96)", n, "elements", 8 * n + 12 * nnz + 4 * rows,
+       lambda: csr(0.96, 1), f"S read ONCE: 8 B per element + 12 B per kept edge ({nnz} edges, {nnz / n:.1%} dense); the fill pass "
+       "replays the keep-mask of the count pass and touches only the sectors of kept entries; includes cudaMalloc of the CSR")
+os.environ["SS_CSR_FILL"] = "tiled"
+report("featurize_csr, round-1 form (count, scan, tiled fill; weighted, alpha=0.96)", n, "elements", 8 * n + 12 * nnz + 4 * rows,
+       lambda: csr(0.96, 1), "same algorithmic bytes, S read twice")
+del os.environ["SS_CSR_FILL"]
+nnz9 = csr(0.8, 1)
+report("featurize_csr (20 % dense: tiled fill; weighted, alpha=0.8)", n, "elements", 8 * n + 12 * nnz9 + 4 * rows,
+       lambda: csr(0.8, 1), f"{nnz9} edges; above 10 % density the fill re-reads S through the transposing tiles")
 del bX, mX
 
 # degrees + spread on C4's Xs / Y
