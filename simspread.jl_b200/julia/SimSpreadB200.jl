@@ -752,7 +752,7 @@ mutable struct ShardedQuery
         return new(r[], comm, blk[])
     end
 end
-close(p::ShardedQuery) = (p.h != C_NULL && ccall((:ss_sharded_destroy, libss), Cint, (Ptr{Cvoid},), p.h); p.h = C_NULL; nothing)
+Base.close(p::ShardedQuery) = (p.h != C_NULL && ccall((:ss_sharded_destroy, libss), Cint, (Ptr{Cvoid},), p.h); p.h = C_NULL; nothing)
 
 # predict for the query rows owned by this rank: Xq = this rank's query-row slab (may be empty), Xs replicated,
 # Y = the full label block (the rank's target-column block is cut out here).  Returns R[rank's queries, all targets].
