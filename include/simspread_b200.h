@@ -224,6 +224,12 @@ SS_API int32_t ss_ipc_close(ss_ctx* ctx, void* devptr);
  * context stream.  kt_out (optional) receives the target degrees used by clean!. */
 SS_API int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
                          uint32_t flags, ss_ivec* kt_out);
+/* The same chain with the result delivered to host memory [the `F[names(ytest,1), names(ytest,2)]` that
+ * predict returns, src/core.jl:423]: the second product runs in column blocks and each finished block is copied to
+ * `host` (column-major, leading dimension ld_host; staged by several host threads when the memory is pageable) while
+ * the next block is computed.  Bit-identical to ss_predict_query + ss_mat_download; R keeps the device copy. */
+SS_API int32_t ss_predict_query_fetch(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
+                                      uint32_t flags, double* host, int64_t ld_host);
 /* k-fold cross-validation in one call (the user-side loop of docs/src/api.md:17-21 over construct / predict /
  * clean!).  X: featurized N x N similarity matrix, Y: N' x Nt labels (both resident).  For fold f the
  * queries are rows q_idx[q_ptr[f] .. q_ptr[f+1]) of X, the sources rows s_idx[s_ptr[f] ..) of X with their label rows

@@ -103,6 +103,7 @@ SIGNATURES = {
     "ss_ipc_open": (c_i32, [vp, vp, P(vp)]),
     "ss_ipc_close": (c_i32, [vp, vp]),
     "ss_predict_query": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
+    "ss_predict_query_fetch": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp, c_i64]),
     "ss_predict_query_folds": (c_i32, [vp, vp, vp, c_i32, vp, vp, vp, vp, vp, vp, vp, vp, c_u32]),
     "ss_predict_query_csr": (c_i32, [vp, vp, vp, vp, vp, c_u32, vp]),
     "ss_predict_source": (c_i32, [vp, vp, vp, vp, c_u32]),

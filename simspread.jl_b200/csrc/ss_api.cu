@@ -370,9 +370,14 @@ static void parallel_copy_cols(char* dst, size_t dpitch, const char* src, size_t
     });
 }
 
+// `ready` / `ready_cols` (download only): columns [i * ready_cols, (i + 1) * ready_cols) of the device matrix are complete
+// once event ready[i] has fired -- the copy stream waits for it instead of draining the compute stream first, so the
+// download of finished column blocks overlaps the kernels that produce the next ones.  `cchunk_cols` overrides the
+// number of columns per staging chunk (it must divide ready_cols).
+static constexpr size_t kStage = size_t(128) << 20;
 static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host, int64_t ldh, int64_t rows, int64_t cols,
-                             bool upload) {
-    constexpr size_t kStage = size_t(128) << 20;
+                             bool upload, const cudaEvent_t* ready = nullptr, int64_t ready_cols = 0,
+                             int64_t cchunk_cols = 0) {
     constexpr int kBufs = 3;
     const size_t row_bytes = size_t(rows) * 8;
     if (row_bytes > kStage || rows == 0 || cols == 0) {  // a single column does not fit a staging buffer: direct copy
@@ -389,9 +394,9 @@ static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host
     }
     std::lock_guard<std::mutex> pool_guard(g_copy_pool_mutex);
     const int nthreads = copy_pool().size();
-    const int64_t cchunk = std::max<int64_t>(1, int64_t(kStage / row_bytes));
+    const int64_t cchunk = cchunk_cols > 0 ? cchunk_cols : std::max<int64_t>(1, int64_t(kStage / row_bytes));
     cudaStream_t st = upload ? ctx->copy_in : ctx->copy_out;
-    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));  // order against work already queued on the compute stream
+    if (!ready) SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));  // order against work already queued on the compute stream
     if (upload) {
         int b = 0;
         for (int64_t c0 = 0; c0 < cols; c0 += cchunk, b = (b + 1) % kBufs) {
@@ -410,8 +415,10 @@ static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host
         auto issue = [&](int64_t i) -> cudaError_t {
             const int b = int(i % kBufs);
             const int64_t c0 = i * cchunk, nc = std::min(cchunk, cols - c0);
-            cudaError_t e = cudaMemcpy2DAsync(ctx->stage[b], row_bytes, dev + c0 * ldd, size_t(ldd) * 8, row_bytes, size_t(nc),
-                                              cudaMemcpyDeviceToHost, st);
+            cudaError_t e = ready ? cudaStreamWaitEvent(st, ready[(c0 + nc - 1) / ready_cols], 0) : cudaSuccess;
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(ctx->stage[b], row_bytes, dev + c0 * ldd, size_t(ldd) * 8, row_bytes, size_t(nc),
+                                      cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[b], st);
             return e;
         };
@@ -923,6 +930,70 @@ int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const 
         SS_CHECK_CUDA(cudaMemcpyAsync(kt_out->d, w.kt, size_t(Y->cols) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
+}
+
+// predict + clean! with the result delivered to HOST memory: the second product runs in column blocks and every
+// finished block is copied out (through the staging buffers when `host` is pageable) while the next one is computed.
+// Bit-identical to ss_predict_query + ss_mat_download (the K loop of an entry does not depend on its tile); R keeps the
+// device copy.  This is the call behind host.predict() / SimSpreadB200.predict when the whole query block is asked for.
+int32_t ss_predict_query_fetch(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R, uint32_t flags,
+                               double* host, int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(Xq && Xs && Y && R && host, "ss_predict_query_fetch: null argument");
+    SS_REQUIRE(Xq->cols == Xs->cols, "Number of features between test and training sets doesn't match");
+    SS_REQUIRE(Xs->rows == Y->rows, "Labels and features have different number of source nodes");
+    SS_REQUIRE(R->rows == Xq->rows && R->cols == Y->cols, "ss_predict_query_fetch: R must be Nq x Nt");
+    SS_REQUIRE(ld_host >= R->rows, "ss_predict_query_fetch: leading dimension too small");
+    const int64_t nq = R->rows, nt = R->cols;
+    if (nq == 0 || nt == 0) return SS_OK;
+    const uint32_t prec = flags & SS_PRECISION_MASK;
+    const size_t row_bytes = size_t(nq) * 8;
+    const bool degenerate = Xs->rows == 0 || Xs->cols == 0;
+    // columns per staging chunk (a multiple of the GEMM's column tile) and per GEMM launch (>= ~20 waves of tiles)
+    const int64_t cchunk = int64_t(kStage / row_bytes) & ~int64_t(127);
+    if (degenerate || prec == SS_PRECISION_F64_INT8 || cchunk < 128 || nt < 4 * cchunk ||
+        row_bytes * size_t(nt) < size_t(kStagedCopyMinBytes)) {
+        SS_TRY(ss_predict_query(ctx, Xq, Xs, Y, R, flags, nullptr));
+        return ss_mat_download(ctx, R, host, ld_host);
+    }
+    const int64_t tiles_chunk = ceil_div(nq, 128) * (cchunk / 128);
+    const int64_t per_block = std::max<int64_t>(1, ceil_div(int64_t(20) * ctx->sm_count, tiles_chunk));
+    const int64_t bcols = cchunk * per_block;
+    const int64_t nblocks = ceil_div(nt, bcols);
+    ChainWs w;
+    SS_TRY(chain_front(ctx, Xs, Y, &w, prec));
+    std::vector<cudaEvent_t> ready(size_t(nblocks), nullptr);
+    int32_t status = SS_OK;
+    auto run = [&]() -> int32_t {
+        for (int64_t b = 0; b < nblocks; ++b) SS_CHECK_CUDA(cudaEventCreateWithFlags(&ready[size_t(b)], cudaEventDisableTiming));
+        for (int64_t b = 0; b < nblocks; ++b) {
+            const int64_t c0 = b * bcols, nc = std::min(bcols, nt - c0);
+            SS_TRY(chain_gemm(ctx, prec, SS_OP_N, Xq->d, Xq->ld, w.T + c0 * w.ldt, w.ldt, R->d + c0 * R->ld, R->ld, nq, nc,
+                              Xq->cols, nullptr, (flags & SS_PREDICT_CLEAN) ? w.kt + c0 : nullptr));
+            SS_CHECK_CUDA(cudaEventRecord(ready[size_t(b)], ctx->stream));
+        }
+        if (host_is_pageable(host)) {
+            SS_TRY(staged_copy2d(ctx, R->d, R->ld, host, ld_host, nq, nt, false, ready.data(), bcols, cchunk));
+        } else {
+            for (int64_t b = 0; b < nblocks; ++b) {
+                const int64_t c0 = b * bcols, nc = std::min(bcols, nt - c0);
+                SS_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_out, ready[size_t(b)], 0));
+                SS_TRY(copy2d(ctx, ctx->copy_out, host + c0 * ld_host, ld_host, R->d + c0 * R->ld, R->ld, nq, nc,
+                              cudaMemcpyDeviceToHost));
+            }
+            SS_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_out));
+        }
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SS_OK;
+    };
+    status = run();
+    if (status != SS_OK) {  // drain before the events go away
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_out);
+    }
+    for (cudaEvent_t e : ready)
+        if (e) cudaEventDestroy(e);
+    return status;
 }
 
 // k-fold cross-validation in one call (the loop of docs/src/api.md:17-21): per fold the blocks

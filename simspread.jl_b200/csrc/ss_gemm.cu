@@ -371,10 +371,10 @@ int32_t make_map(CUtensorMap* map, const double* base, int64_t dim0, int64_t dim
 
 namespace ss {
 
-int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B,
-                        int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                        const int32_t* row_div, const int32_t* col_flag, bool accumulate, int nmirror,
-                        double* const* mirrors) {
+static int32_t launch_gemm_f64_one(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B,
+                                   int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                   const int32_t* row_div, const int32_t* col_flag, bool accumulate, int nmirror,
+                                   double* const* mirrors) {
     SS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem (M=%lld N=%lld K=%lld)", (long long)M,
                (long long)N, (long long)K);
     SS_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
@@ -438,6 +438,31 @@ int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, cons
         ctx->prof.push_back(rec);
     }
     ctx->launches++;
+    return SS_OK;
+}
+
+// K-blocking (off by default, SS_GEMM_KBLOCK=<k>): the product is run as ceil(K / k) launches that accumulate into C, so
+// that the A panels of one wave (16 row tiles x 128 rows x k x 8 B) stay in L2 between the column tiles that re-read
+// them.  The split depends on K alone, so every caller (whole matrix, slab, shard) rounds the same way.  Not used with
+// the row division (it applies to the complete sum) nor with mirrors.
+int32_t launch_gemm_f64(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                        const int32_t* row_div, const int32_t* col_flag, bool accumulate, int nmirror,
+                        double* const* mirrors) {
+    int64_t kb = 0;
+    if (const char* env = getenv("SS_GEMM_KBLOCK")) kb = atoll(env) & ~int64_t(15);
+    if (kb < 256 || K < 2 * kb || row_div || nmirror)
+        return launch_gemm_f64_one(ctx, opA, A, lda, B, ldb, C, ldc, M, N, K, row_div, col_flag, accumulate, nmirror,
+                                   mirrors);
+    const int64_t nblk = (K + kb - 1) / kb;
+    const int64_t step = (((K + nblk - 1) / nblk) + 15) & ~int64_t(15);  // even blocks, 16-aligned starts
+    for (int64_t k0 = 0; k0 < K; k0 += step) {
+        const int64_t kk = (K - k0 < step) ? (K - k0) : step;
+        const bool last = (k0 + kk >= K);
+        const double* Ab = (opA == SS_OP_N) ? A + k0 * lda : A + k0;
+        SS_TRY(launch_gemm_f64_one(ctx, opA, Ab, lda, B + k0, ldb, C, ldc, M, N, kk, nullptr, last ? col_flag : nullptr,
+                                   accumulate || k0 > 0, 0, nullptr));
+    }
     return SS_OK;
 }
 

@@ -587,10 +587,18 @@ def predict(*args, GPU: bool = False, clean: bool = False, layout: str = "auto",
     out = None
     if is_q.any():
         R = DMat(ctx, len(g.queries), nt)
+        whole = (is_q.all() and all_cols and len(rows) == R.rows
+                 and np.array_equal(ri, np.arange(R.rows, dtype=np.int32)))
         if len(g.features) and len(g.sources):
             use_sparse = layout == "sparse"
             if layout == "auto":  # density from the degree kernels (one pass), not from a CSR build
                 use_sparse = max(g.density()) < SPARSE_DENSITY_THRESHOLD
+            if not use_sparse and whole:
+                # the whole query block, dense chain: the download of finished column blocks overlaps the product
+                out = np.empty((R.rows, nt), order="F")
+                check(lib().ss_predict_query_fetch(ctx.h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, out.ctypes.data, R.rows))
+                g.last_layout = "dense"
+                return NamedArray(out, (rows, cols))
             if use_sparse:
                 cq, cs = g.csr()
                 check(lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, g.Y.h, R.h, flags, None))

@@ -331,6 +331,14 @@ function _predict_graph(A::Graph, B::Graph, rows, cols; clean::Bool=false, preci
         R = DMat(length(g.queries), nt)
         if !isempty(g.features) && !isempty(g.sources)
             sparse = layout == :sparse || (layout == :auto && max(_density(g.Xq), _density(g.Xs)) < SPARSE_DENSITY_THRESHOLD)
+            if !sparse && all(isq) && ri == collect(1:R.rows) && ci == collect(1:nt)
+                # the whole query block on the dense chain: finished column blocks are downloaded while the next ones
+                # are computed (out is column-major with leading dimension R.rows)
+                GC.@preserve out check(ccall((:ss_predict_query_fetch, libss), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Ptr{Float64}, Int64),
+                    ctx().h, g.Xq.h, g.Xs.h, g.Y.h, R.h, flags, out, Int64(R.rows)))
+                return NamedArray(out, (string.(rows), string.(cols)))
+            end
             if sparse
                 cq = DCsr(g.Xq, -Inf, true)
                 cs = DCsr(g.Xs, -Inf, true; by_columns=true)

@@ -417,6 +417,76 @@ def test_predict_query_host_pipelined(ss, o, nq, ns, nf, nt, slab):
     assert np.all(R[nq:] == 7.0)
 
 
+@pytest.mark.parametrize("nq,ns,nf,nt", [(20000, 256, 256, 3500), (40, 24, 24, 10)])
+def test_predict_query_fetch_overlapped_download(ss, o, nq, ns, nf, nt):
+    """ss_predict_query_fetch (second product in column blocks, each block downloaded while the next is computed) is
+    bit-identical to ss_predict_query + download, into pageable memory (staging buffers) and into pinned memory, with a
+    padded leading dimension; the large shape takes the block path, the small one the plain path."""
+    import ctypes as C
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=9, y_density=0.05, alpha=0.3, weighted=True)
+    Y[:, 1 % nt] = 0.0
+    ctx, L = ss.Context.default(), ss.lib()
+    dq, dx, dy = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y))
+    R = ss.DMat(ctx, nq, nt)
+    check(L.ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+    want = R.to_host()
+    sub = slice(0, min(nq, 64))
+    ref = o.predict_blocks_query(Xq[sub], Xs, Y)
+    o.clean_blocks(ref, o.degrees_blocks(Xs, Y)[2])
+    assert relerr(want[sub], ref) < RTOL
+    # pageable destination, ld > rows
+    R2 = ss.DMat(ctx, nq, nt)
+    out = np.full((nq + 5, nt), 7.0, order="F")
+    check(L.ss_predict_query_fetch(ctx.h, dq.h, dx.h, dy.h, R2.h, SS_PREDICT_CLEAN, out.ctypes.data, nq + 5))
+    assert np.array_equal(out[:nq], want) and np.all(out[nq:] == 7.0)
+    assert np.array_equal(R2.to_host(), want)  # the device copy is complete as well
+    # pinned destination
+    p = C.c_void_p()
+    check(L.ss_host_alloc(nq * nt * 8, C.byref(p)))
+    try:
+        check(L.ss_predict_query_fetch(ctx.h, dq.h, dx.h, dy.h, R2.h, SS_PREDICT_CLEAN, p, nq))
+        got = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(nt, nq)).T
+        assert np.array_equal(got, want)
+    finally:
+        L.ss_host_free(p)
+    # the host layer takes this route for the whole query block
+    qn, sn = [f"q{i}" for i in range(nq)], [f"s{i}" for i in range(ns)]
+    fn, tn = [f"f{i}" for i in range(nf)], [f"t{i}" for i in range(nt)]
+    A, B = ss.construct((ss.NamedArray(Y, (sn, tn)), ss.NamedArray(np.zeros((nq, nt)), (qn, tn))),
+                        (ss.NamedArray(Xs, (sn, fn)), ss.NamedArray(Xq, (qn, fn))))
+    yh = ss.predict((A, B), ss.NamedArray(np.zeros((nq, nt)), (qn, tn)), clean=True, layout="dense")
+    assert np.array_equal(yh.array, want)
+
+
+def test_gemm_k_blocking_switch(ss, o):
+    """SS_GEMM_KBLOCK (experiment switch, off by default) runs the second product as accumulating launches over blocks
+    of the feature dimension; clean! is applied by the last block only."""
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    nq, ns, nf, nt = 300, 200, 1100, 260
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=4, y_density=0.05, alpha=0.3, weighted=True)
+    Y[:, 3] = 0.0
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    ctx = ss.Context.default()
+    dq, dx, dy = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y))
+    R = ss.DMat(ctx, nq, nt)
+    os.environ["SS_GEMM_KBLOCK"] = "256"
+    try:
+        l0 = ctx.launch_count()
+        check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+        blocked_launches = ctx.launch_count() - l0
+    finally:
+        os.environ.pop("SS_GEMM_KBLOCK", None)
+    l0 = ctx.launch_count()
+    R1 = ss.DMat(ctx, nq, nt)
+    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R1.h, SS_PREDICT_CLEAN, None))
+    assert blocked_launches > ctx.launch_count() - l0
+    got = R.to_host()
+    assert relerr(got, want) < RTOL
+    assert np.array_equal(got == -99, want == -99)
+
+
 def test_empty_and_degenerate_inputs(ss, o):
     from simspread_b200._lib import check
     ctx = ss.Context.default()
