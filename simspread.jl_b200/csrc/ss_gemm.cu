@@ -96,11 +96,27 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles
     return {first_m + r % gm, r / gm};
 }
 
+// Work units.  Whole waves are 128 x 128 tiles; the tiles of the last, partial wave are cut into `tail_split` row
+// bands of 128 / tail_split rows so that the SMs a partial wave would leave idle get work too (C3 shape: 640 tiles
+// = 4 waves + 48 tiles -> 96 half tiles, 4.5 instead of 5 tile times).  A band is computed by the same 2 x 4 warp
+// grid with a shorter warp tile; every output element still accumulates k = 0 .. K-1 in the same DMMA sequence, so
+// the result does not depend on the split (bit-identical to whole tiles).
+struct Unit {
+    int tile, band, split;
+};
+__device__ __forceinline__ Unit unit_of(int u, int full_tiles, int tail_split) {
+    if (u < full_tiles) return {u, 0, 1};
+    const int v = u - full_tiles;
+    return {full_tiles + v / tail_split, v % tail_split, tail_split};
+}
+
 struct GemmParams {
     double* C;
     int64_t ldc;
     int M, N, K;
     int tiles_m, tiles_n;
+    int full_tiles;           // tiles [0, full_tiles) are whole waves of 128 x 128 tiles
+    int tail_split;           // the remaining tiles are cut into 1 / 2 / 4 row bands, one band per work unit
     const int32_t* row_div;   // optional: C[m,:] = acc / row_div[m] (0 when row_div[m] == 0)
     const int32_t* col_flag;  // optional: C[:,n] = -99 when col_flag[n] == 0
     int accumulate;           // C += result
@@ -131,6 +147,120 @@ __device__ __forceinline__ double finish(double acc, int row, int col, const Gem
     return v;
 }
 
+// One work unit of the consumer warps: the (MT_ * 16) x 128 row band `band` of tile (m0, n0), warp tile (MT_ * 8) x 32.
+// MT_ = 8 is the whole tile.
+template <bool A_MMAJOR, int MT_>
+__device__ __forceinline__ void consume_unit(const GemmParams& p, uint32_t smem_base, uint32_t bar_base, int m0, int n0,
+                                             int band, int kblocks, int warp, int lane, int& stage, uint32_t& phase) {
+    const int g = lane >> 2, t = lane & 3;
+    const int rg = rho(g);
+    const int m_warp = band * (2 * MT_ * 8) + (warp / WARPS_N) * (MT_ * 8);
+    const int n_warp = (warp % WARPS_N) * WN;
+
+    // per-thread shared-memory offsets (bytes, relative to the stage's A / B base)
+    // B (k-major): row n = n_warp + 8j + rho(g); chunk (t + 4h) ^ rho(g)
+    uint32_t offB[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) offB[h] = (n_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
+    // A k-major: row m = m_warp + 8i + rho(g), same chunk rule
+    uint32_t offAk[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) offAk[h] = (m_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
+    // A m-major: block (m_warp/16 + b), row k = 2t + (s&1) + 8(s>>1), chunk g ^ (k & 7)
+    uint32_t offAm[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int k = 2 * t + (s & 1) + 8 * (s >> 1);
+        offAm[s] = (m_warp >> 4) * 2048 + k * 128 + ((g ^ (k & 7)) << 4);
+    }
+
+    double acc[MT_][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT_; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        const uint32_t sA = smem_base + stage * STAGE_BYTES;
+        const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double2 bf[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = lds128(sB + offB[h] + j * 8 * 128);
+            if (A_MMAJOR) {
+#pragma unroll
+                for (int ss2 = 0; ss2 < 2; ++ss2) {
+                    const int s = 2 * h + ss2;
+                    double2 af[MT_ / 2];
+#pragma unroll
+                    for (int b = 0; b < MT_ / 2; ++b) af[b] = lds128(sA + offAm[s] + b * 2048);
+#pragma unroll
+                    for (int b = 0; b < MT_ / 2; ++b)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const double bv = ss2 ? bf[j].y : bf[j].x;
+                            dmma(acc[2 * b][j], af[b].x, bv);
+                            dmma(acc[2 * b + 1][j], af[b].y, bv);
+                        }
+                }
+            } else {
+                double2 af[MT_];
+#pragma unroll
+                for (int i = 0; i < MT_; ++i) af[i] = lds128(sA + offAk[h] + i * 8 * 128);
+#pragma unroll
+                for (int ss2 = 0; ss2 < 2; ++ss2)
+#pragma unroll
+                    for (int i = 0; i < MT_; ++i)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j)
+                            dmma(acc[i][j], ss2 ? af[i].y : af[i].x, ss2 ? bf[j].y : bf[j].x);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+
+    // ---- epilogue: registers -> global (column-major C), fused normalisation / clean! ----
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = n0 + n_warp + 8 * j + t + 4 * e;  // rho(2t+e) = t + 4e
+            if (col >= p.N) continue;
+            const int64_t coff = int64_t(col) * p.ldc;
+            const double* ccol = p.C + coff;
+            if (A_MMAJOR) {
+#pragma unroll
+                for (int b = 0; b < MT_ / 2; ++b) {
+                    const int row = m0 + m_warp + 16 * b + 2 * g;  // rows (row, row+1)
+                    if (row + 1 < p.M && p.cvec) {
+                        double2 v;
+                        v.x = finish(acc[2 * b][j][e], row, col, p, ccol + row);
+                        v.y = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
+                        store2(p, coff + row, v);
+                    } else {
+                        if (row < p.M) store1(p, coff + row, finish(acc[2 * b][j][e], row, col, p, ccol + row));
+                        if (row + 1 < p.M)
+                            store1(p, coff + row + 1,
+                                   finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < MT_; ++i) {
+                    const int row = m0 + m_warp + 8 * i + rg;
+                    if (row < p.M) store1(p, coff + row, finish(acc[i][j][e], row, col, p, ccol + row));
+                }
+            }
+        }
+}
+
 // A_MMAJOR: A is M x K column-major (m contiguous) staged as 8 boxes [16 k][16 m] per slab.
 // !A_MMAJOR: A is stored K x M column-major (k contiguous) staged as one box [128 m][16 k].
 template <bool A_MMAJOR>
@@ -143,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int kblocks = (p.K + BK - 1) / BK;
-    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int total_units = p.full_tiles + (p.tiles_m * p.tiles_n - p.full_tiles) * p.tail_split;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -160,9 +290,14 @@ __global__ void __launch_bounds__(THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             int checkpoint = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = tile_coord(tile, p.tiles_m, p.tiles_n);
-                const int m0 = tc.tm * BM, n0 = tc.tn * BN;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const Unit un = unit_of(u, p.full_tiles, p.tail_split);
+                const TileCoord tc = tile_coord(un.tile, p.tiles_m, p.tiles_n);
+                const int n0 = tc.tn * BN;
+                // rows of A this unit needs: the whole tile, or one band of it (multiples of 16 rows)
+                const int band_rows = BM / un.split;
+                const int m0 = tc.tm * BM + un.band * band_rows;
+                const uint32_t a_off = uint32_t(un.band * band_rows) * (BK * 8);  // both layouts: 128 bytes per row
                 for (int kb = 0; kb < kblocks; ++kb) {
                     if (p.sync_prog && (kb % SYNC_CHUNK) == 0) {
                         // Loose lockstep.  The 148 CTAs of a wave share ~25 A/B panels through L2
@@ -187,15 +322,26 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const uint32_t full = bar_base + 8 * stage;
                     const uint32_t empty = bar_base + 8 * (STAGES + stage);
                     mbar_wait(empty, phase ^ 1);
-                    mbar_expect_tx(full, STAGE_BYTES);
                     const uint32_t sA = smem_base + stage * STAGE_BYTES;
                     const uint32_t sB = sA + A_BYTES;
-                    if (A_MMAJOR) {
+                    if (un.split == 1) {
+                        mbar_expect_tx(full, STAGE_BYTES);
+                        if (A_MMAJOR) {
 #pragma unroll
-                        for (int b = 0; b < BM / 16; ++b)
-                            tma_load_2d(sA + b * 2048, &mapA, m0 + b * 16, kb * BK, full);
+                            for (int b = 0; b < BM / 16; ++b)
+                                tma_load_2d(sA + b * 2048, &mapA, m0 + b * 16, kb * BK, full);
+                        } else {
+                            tma_load_2d(sA, &mapA, kb * BK, m0, full);
+                        }
+                    } else if (A_MMAJOR) {
+                        // a band is band_rows / 16 of the 16-row boxes, placed where the whole tile would have them
+                        mbar_expect_tx(full, B_BYTES + band_rows * BK * 8);
+                        for (int b = 0; b < band_rows / 16; ++b)
+                            tma_load_2d(sA + a_off + b * 2048, &mapA, m0 + b * 16, kb * BK, full);
                     } else {
-                        tma_load_2d(sA, &mapA, kb * BK, m0, full);
+                        // k-major A has one 128-row box: load it whole, the consumers read their band of it
+                        mbar_expect_tx(full, STAGE_BYTES);
+                        tma_load_2d(sA, &mapA, kb * BK, tc.tm * BM, full);
                     }
                     tma_load_2d(sB, &mapB, kb * BK, n0, full);
                     if (++stage == STAGES) {
@@ -210,119 +356,18 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
 
     // ================= DMMA consumers =================
-    const int g = lane >> 2, t = lane & 3;
-    const int rg = rho(g);
-    const int m_warp = (warp / WARPS_N) * WM;
-    const int n_warp = (warp % WARPS_N) * WN;
-
-    // per-thread shared-memory offsets (bytes, relative to the stage's A / B base)
-    // B (k-major): row n = n_warp + 8j + rho(g); chunk (t + 4h) ^ rho(g)
-    uint32_t offB[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) offB[h] = (n_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
-    // A k-major: row m = m_warp + 8i + rho(g), same chunk rule
-    uint32_t offAk[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) offAk[h] = (m_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
-    // A m-major: block (m_warp/16 + b), row k = 2t + (s&1) + 8(s>>1), chunk g ^ (k & 7)
-    uint32_t offAm[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int k = 2 * t + (s & 1) + 8 * (s >> 1);
-        offAm[s] = (m_warp >> 4) * 2048 + k * 128 + ((g ^ (k & 7)) << 4);
-    }
-
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(tile, p.tiles_m, p.tiles_n);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const Unit un = unit_of(u, p.full_tiles, p.tail_split);
+        const TileCoord tc = tile_coord(un.tile, p.tiles_m, p.tiles_n);
         const int m0 = tc.tm * BM, n0 = tc.tn * BN;
-
-        double acc[MT][NT][2];
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(bar_base + 8 * stage, phase);
-            const uint32_t sA = smem_base + stage * STAGE_BYTES;
-            const uint32_t sB = sA + A_BYTES;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double2 bf[NT];
-#pragma unroll
-                for (int j = 0; j < NT; ++j) bf[j] = lds128(sB + offB[h] + j * 8 * 128);
-                if (A_MMAJOR) {
-#pragma unroll
-                    for (int ss2 = 0; ss2 < 2; ++ss2) {
-                        const int s = 2 * h + ss2;
-                        double2 af[MT / 2];
-#pragma unroll
-                        for (int b = 0; b < MT / 2; ++b) af[b] = lds128(sA + offAm[s] + b * 2048);
-#pragma unroll
-                        for (int b = 0; b < MT / 2; ++b)
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                const double bv = ss2 ? bf[j].y : bf[j].x;
-                                dmma(acc[2 * b][j], af[b].x, bv);
-                                dmma(acc[2 * b + 1][j], af[b].y, bv);
-                            }
-                    }
-                } else {
-                    double2 af[MT];
-#pragma unroll
-                    for (int i = 0; i < MT; ++i) af[i] = lds128(sA + offAk[h] + i * 8 * 128);
-#pragma unroll
-                    for (int ss2 = 0; ss2 < 2; ++ss2)
-#pragma unroll
-                        for (int i = 0; i < MT; ++i)
-#pragma unroll
-                            for (int j = 0; j < NT; ++j)
-                                dmma(acc[i][j], ss2 ? af[i].y : af[i].x, ss2 ? bf[j].y : bf[j].x);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
-            if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
-            }
-        }
-
-        // ---- epilogue: registers -> global (column-major C), fused normalisation / clean! ----
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = n0 + n_warp + 8 * j + t + 4 * e;  // rho(2t+e) = t + 4e
-                if (col >= p.N) continue;
-                const int64_t coff = int64_t(col) * p.ldc;
-                const double* ccol = p.C + coff;
-                if (A_MMAJOR) {
-#pragma unroll
-                    for (int b = 0; b < MT / 2; ++b) {
-                        const int row = m0 + m_warp + 16 * b + 2 * g;  // rows (row, row+1)
-                        if (row + 1 < p.M && p.cvec) {
-                            double2 v;
-                            v.x = finish(acc[2 * b][j][e], row, col, p, ccol + row);
-                            v.y = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
-                            store2(p, coff + row, v);
-                        } else {
-                            if (row < p.M) store1(p, coff + row, finish(acc[2 * b][j][e], row, col, p, ccol + row));
-                            if (row + 1 < p.M)
-                                store1(p, coff + row + 1,
-                                       finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1));
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < MT; ++i) {
-                        const int row = m0 + m_warp + 8 * i + rg;
-                        if (row < p.M) store1(p, coff + row, finish(acc[i][j][e], row, col, p, ccol + row));
-                    }
-                }
-            }
+        if (un.split == 1)
+            consume_unit<A_MMAJOR, 8>(p, smem_base, bar_base, m0, n0, 0, kblocks, warp, lane, stage, phase);
+        else if (un.split == 2)
+            consume_unit<A_MMAJOR, 4>(p, smem_base, bar_base, m0, n0, un.band, kblocks, warp, lane, stage, phase);
+        else
+            consume_unit<A_MMAJOR, 2>(p, smem_base, bar_base, m0, n0, un.band, kblocks, warp, lane, stage, phase);
     }
 }
 
@@ -409,7 +454,23 @@ static int32_t launch_gemm_f64_one(ss_ctx* ctx, int opA, const double* A, int64_
         if (reinterpret_cast<uintptr_t>(mirrors[i]) & 15) p.cvec = 0;
     const int64_t total = int64_t(p.tiles_m) * p.tiles_n;
     SS_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
-    const int grid = int(total < ctx->sm_count ? total : ctx->sm_count);
+    // partial last wave: cut its tiles into 2 or 4 row bands when that fills more SMs (see Unit); SS_GEMM_TAIL_SPLIT=0
+    // keeps whole tiles (A/B measurements)
+    const int64_t sms = ctx->sm_count;
+    const int64_t rem = total % sms;
+    int split = 1;
+    {
+        const char* e = getenv("SS_GEMM_TAIL_SPLIT");
+        const int allow = e ? atoi(e) : 4;
+        if (rem > 0 && K >= 64) {
+            if (allow >= 4 && rem * 4 <= sms) split = 4;
+            else if (allow >= 2 && rem * 2 <= sms) split = 2;
+        }
+    }
+    p.tail_split = split;
+    p.full_tiles = int(split > 1 ? total - rem : total);
+    const int64_t units = p.full_tiles + (total - p.full_tiles) * split;
+    const int grid = int(units < sms ? units : sms);
     if (total > grid) {  // more than one wave: keep the waves in lockstep for L2 reuse
         if (!ctx->tile_counter) SS_CHECK_CUDA(cudaMalloc(&ctx->tile_counter, 4096));
         SS_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, size_t(grid) * 4, ctx->stream));

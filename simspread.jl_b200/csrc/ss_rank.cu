@@ -115,19 +115,43 @@ __global__ void __launch_bounds__(WT_TPB)
         cnt[q] = 0;
     }
     // The next tile is loaded into registers while the current one is scanned (the loads used to sit between two
-    // barriers with nothing to overlap them: 44 % of HBM).  Warp w takes columns w, w+8, ...; lane = row (256 B
-    // contiguous per column); out-of-range cells read a clamped, valid address and are ignored by the scan.
+    // barriers with nothing to overlap them).  Warp w takes columns w, w+8, ...; lane = row (256 B contiguous per
+    // column); out-of-range cells read a clamped, valid address and are ignored by the scan.
     constexpr int WT_PER = WT_COLS / (WT_TPB / 32);
     double pre[WT_PER];
     const int64_t rl = min(row0 + lane, rows - 1);
     auto prefetch = [&](int64_t c0) {
+        if (c0 + WT_COLS <= cols) {  // whole tile in range: one pointer, constant stride
+            const double* pc = R + (c0 + warp) * ld + rl;
+            const int64_t step = int64_t(WT_TPB / 32) * ld;
 #pragma unroll
-        for (int j = 0; j < WT_PER; ++j) {
-            const int64_t c = min(c0 + warp + j * (WT_TPB / 32), cols - 1);
-            pre[j] = __ldg(R + c * ld + rl);
+            for (int j = 0; j < WT_PER; ++j) pre[j] = __ldg(pc + j * step);
+        } else {
+#pragma unroll
+            for (int j = 0; j < WT_PER; ++j) {
+                const int64_t c = min(c0 + warp + j * (WT_TPB / 32), cols - 1);
+                pre[j] = __ldg(R + c * ld + rl);
+            }
         }
     };
     prefetch(0);
+    // Filter state of the four rows of this warp.  Once a list is full a cell qualifies iff its key beats the key of
+    // rank L-1.  For non-NaN values the key order is the numeric order with -0.0 < +0.0, so the filter is ONE FP64
+    // compare per cell, !(v <= tv) (true for v > tv and for NaN, whose key is the largest), instead of the 64-bit key
+    // transform + integer compare; the two thresholds where that differs from the key order (tv = -0.0: a +0.0 cell
+    // beats it; tv = NaN: nothing beats it) switch the row to the exact key compare.  Survivors are re-checked against
+    // the exact keys when they are ranked, so the filter only has to let every qualifying cell through.
+    constexpr uint64_t KEY_NEGZERO = 0x7FFFFFFFFFFFFFFFull, KEY_NAN = 0xFFFFFFFFFFFFFFFFull;
+    double tv[4];
+    bool full[4], live[4], exact[4];
+    auto refresh = [&](int q) {
+        const uint64_t thr = __shfl_sync(0xffffffffu, lkey[q], L - 1);  // key of rank L-1 once the list is full
+        full[q] = cnt[q] >= L;
+        tv[q] = key_to_value(thr);
+        exact[q] = full[q] && (thr == KEY_NEGZERO || thr == KEY_NAN);
+    };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) live[q] = row0 + 4 * warp + q < rows;  // warp-uniform
     for (int64_t c0 = 0; c0 < cols; c0 += WT_COLS) {
         const int nc = int(min(int64_t(WT_COLS), cols - c0));
         __syncthreads();
@@ -136,25 +160,26 @@ __global__ void __launch_bounds__(WT_TPB)
         __syncthreads();
         if (c0 + WT_COLS < cols) prefetch(c0 + WT_COLS);
         // the four rows of this warp are independent chains: issue their loads / ballots together
-        uint64_t thr[4];
-        bool full[4], live[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            thr[q] = __shfl_sync(0xffffffffu, lkey[q], L - 1);  // key of rank L-1 once the list is full
-            full[q] = cnt[q] >= L;
-            live[q] = row0 + 4 * warp + q < rows;               // warp-uniform
-        }
+        for (int q = 0; q < 4; ++q) refresh(q);
         for (int cb = 0; cb < nc; cb += 32) {
             const int c = cb + lane;
             const bool inb = c < nc;
-            uint64_t key[4];
+            double v[4];
             unsigned cand[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                key[q] = (inb && live[q]) ? isless_key(wt_tile[(4 * warp + q) * (WT_COLS + 1) + c]) : 0;
+            for (int q = 0; q < 4; ++q) v[q] = wt_tile[(4 * warp + q) * (WT_COLS + 1) + c];  // c < WT_COLS always
+            if (exact[0] | exact[1] | exact[2] | exact[3]) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                cand[q] = __ballot_sync(0xffffffffu, inb && live[q] && (!full[q] || key[q] > thr[q]));
+                for (int q = 0; q < 4; ++q) {
+                    const uint64_t thr = __shfl_sync(0xffffffffu, lkey[q], L - 1);
+                    cand[q] = __ballot_sync(0xffffffffu, inb && live[q] && (!full[q] || isless_key(v[q]) > thr));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    cand[q] = __ballot_sync(0xffffffffu, inb && live[q] && (!full[q] || !(v[q] <= tv[q])));
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!cand[q]) continue;  // the common case after the first few hundred columns
@@ -162,7 +187,7 @@ __global__ void __launch_bounds__(WT_TPB)
                 while (cd) {
                     const int src = __ffs(cd) - 1;
                     cd &= cd - 1;
-                    const uint64_t ck = __shfl_sync(0xffffffffu, key[q], src);
+                    const uint64_t ck = isless_key(__shfl_sync(0xffffffffu, v[q], src));
                     const int32_t ci = int32_t(c0 + cb + src);
                     // rank = number of list entries with key >= ck (earlier columns win ties)
                     const bool ge = (lane < cnt[q]) && (lkey[q] >= ck);
@@ -179,8 +204,7 @@ __global__ void __launch_bounds__(WT_TPB)
                     }
                     if (cnt[q] < L) ++cnt[q];
                 }
-                thr[q] = __shfl_sync(0xffffffffu, lkey[q], L - 1);
-                full[q] = cnt[q] >= L;
+                refresh(q);
             }
         }
     }

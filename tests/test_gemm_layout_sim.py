@@ -33,10 +33,12 @@ def tma_kmajor(tile):
     return sm
 
 
-def tma_mmajor(tile):
-    """tile[m, k] (128 x 16) -> 8 boxes {16 m, 16 k} of 2 KB each."""
+def tma_mmajor(tile, band=0, split=1):
+    """tile[m, k] (128 x 16) -> 8 boxes {16 m, 16 k} of 2 KB each.  A row band (split 2 / 4) loads only its
+    128 / split rows, into the boxes the whole tile would have put them (producer: a_off + b * 2048)."""
     sm = np.full(128 * 16, np.nan)
-    for b in range(8):
+    per = 8 // split
+    for b in range(band * per, (band + 1) * per):
         for k in range(16):
             for mi in range(16):
                 o = k * 128 + mi * 8
@@ -71,8 +73,9 @@ def mma_8x8x4(acc, a, b):
         acc[lane][1] += C[g, 2 * t + 1]
 
 
-def run_warp(sA, sB, warp, a_mmajor):
-    m_warp = (warp // WARPS_N) * WM
+def run_warp(sA, sB, warp, a_mmajor, MT=MT, band=0):
+    """MT = 8: whole tile; MT = 4 / 2: row band `band` of 64 / 32 rows (consume_unit<A_MMAJOR, MT_>)."""
+    m_warp = band * (2 * MT * 8) + (warp // WARPS_N) * (MT * 8)
     n_warp = (warp % WARPS_N) * WN
     acc = np.zeros((MT, NT, 32, 2))
     for h in range(2):
@@ -118,8 +121,8 @@ def run_warp(sA, sB, warp, a_mmajor):
     return acc
 
 
-def epilogue(C, acc, warp, a_mmajor):
-    m_warp = (warp // WARPS_N) * WM
+def epilogue(C, acc, warp, a_mmajor, MT=MT, band=0):
+    m_warp = band * (2 * MT * 8) + (warp // WARPS_N) * (MT * 8)
     n_warp = (warp % WARPS_N) * WN
     for lane in range(32):
         g, t = lane >> 2, lane & 3
@@ -152,6 +155,59 @@ def test_fragment_layout_reproduces_gemm(a_mmajor):
             acc = run_warp(sA, sB, warp, a_mmajor)
             epilogue(C, acc, warp, a_mmajor)
     assert np.array_equal(C, A @ B)
+
+
+@pytest.mark.parametrize("a_mmajor", [True, False])
+@pytest.mark.parametrize("split", [2, 4])
+def test_row_bands_reproduce_the_tile(a_mmajor, split):
+    """A tile of a partial wave is computed as `split` row bands by the same 2 x 4 warp grid with a shorter warp
+    tile; together the bands must write every entry of the tile exactly once, from the same k sequence."""
+    rng = np.random.default_rng(5)
+    K = 32
+    A = rng.integers(-4, 5, size=(BM, K)).astype(float)
+    B = rng.integers(-4, 5, size=(K, BN)).astype(float)
+    C = np.zeros((BM, BN))
+    writes = np.zeros((BM, BN), dtype=int)
+    mt = 8 // split
+    for band in range(split):
+        for kb in range(K // BK):
+            At = A[:, kb * BK:(kb + 1) * BK]
+            Bt = B[kb * BK:(kb + 1) * BK, :].T
+            sA = tma_mmajor(At, band, split) if a_mmajor else tma_kmajor(At)  # k-major A: the whole box is loaded
+            sB = tma_kmajor(Bt)
+            for warp in range(8):
+                acc = run_warp(sA, sB, warp, a_mmajor, MT=mt, band=band)
+                assert not np.isnan(acc).any()  # a band never reads rows the producer did not load
+                epilogue(C, acc, warp, a_mmajor, MT=mt, band=band)
+                if kb == 0:
+                    W = np.zeros((BM, BN))
+                    epilogue(W, np.ones_like(acc), warp, a_mmajor, MT=mt, band=band)
+                    writes += (W != 0)
+    assert np.array_equal(C, A @ B) and np.all(writes == 1)
+
+
+def test_unit_enumeration_covers_every_tile_once():
+    """Host-side choice of the split (launch_gemm_f64_one) + unit_of: whole waves as tiles, the rest as bands."""
+    sms = 148
+    for total in [1, 6, 37, 38, 74, 75, 147, 148, 149, 169, 210, 222, 640, 148 * 7 + 36]:
+        rem = total % sms
+        split = 4 if (rem and rem * 4 <= sms) else 2 if (rem and rem * 2 <= sms) else 1
+        full = total - rem if split > 1 else total
+        units = full + (total - full) * split
+        seen = {}
+        for u in range(units):
+            if u < full:
+                t, band, sp = u, 0, 1
+            else:
+                v = u - full
+                t, band, sp = full + v // split, v % split, split
+            seen.setdefault(t, []).append((band, sp))
+        assert sorted(seen) == list(range(total))
+        for t, parts in seen.items():
+            sp = parts[0][1]
+            assert sorted(b for b, _ in parts) == list(range(sp))
+        if split > 1:
+            assert units - full <= sms  # the bands of the partial wave fit one round of the grid
 
 
 def test_tile_rasterisation_is_a_bijection():

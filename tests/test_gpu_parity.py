@@ -143,7 +143,7 @@ def test_kat_atL(ss, kats):
 # ---------------------------------------------------------------------------------------------
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 5), (445, 445), (1000, 333), (2049, 130)])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 5), (445, 445), (1000, 333), (2049, 130), (3000, 1500)])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_featurize_dense_and_csr_bit_exact(ss, o, rows, cols, weighted):
     rng = np.random.default_rng(rows * 1000 + cols)
@@ -151,30 +151,37 @@ def test_featurize_dense_and_csr_bit_exact(ss, o, rows, cols, weighted):
     S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = np.nan
     S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = -0.0
     S.flat[rng.integers(0, S.size, size=max(1, S.size // 50))] = 0.35  # exactly alpha: kept (>=)
-    for alpha in (0.35, -0.01, 0.0, 1.01):
+    from simspread_b200._lib import check
+    ctx = ss.Context.default()
+    d = ss.DMat.from_host(ctx, S)
+    for alpha in (0.35, -0.01, 0.0, 1.01, 0.97):
         want = o.cutoff(S, alpha, weighted)
         got = ss.cutoff(S, alpha, weighted)
         assert np.array_equal(got, want)
         assert np.array_equal(np.signbit(got), np.signbit(want))
-        # CSR (warp-ballot compaction)
-        ctx = ss.Context.default()
-        d = ss.DMat.from_host(ctx, S)
-        h = C.c_void_p()
-        from simspread_b200._lib import check
-        check(ss.lib().ss_featurize_csr(ctx.h, d.h, alpha, int(weighted), C.byref(h)))
-        r, c, nnz, hv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
-        check(ss.lib().ss_csr_info(h, C.byref(r), C.byref(c), C.byref(nnz), C.byref(hv)))
-        rp = np.empty(rows + 1, np.int32)
-        ci = np.empty(max(nnz.value, 1), np.int32)
-        va = np.empty(max(nnz.value, 1), np.float64)
-        check(ss.lib().ss_csr_download(ctx.h, h, rp.ctypes.data, ci.ctypes.data, va.ctypes.data if hv.value else None))
-        ss.lib().ss_csr_destroy(h)
         wr, wc = np.nonzero(want != 0)  # row-major order == CSR order
-        assert nnz.value == len(wr) and bool(hv.value) == weighted
-        assert np.array_equal(rp, np.concatenate(([0], np.cumsum(np.bincount(wr, minlength=rows)))).astype(np.int32))
-        assert np.array_equal(ci[:nnz.value], wc.astype(np.int32))
-        if weighted:
-            assert np.array_equal(va[:nnz.value], want[wr, wc])
+        # CSR: count + keep-mask with lanes along rows, device-wide scan of the (row, segment) counts, then either
+        # fill (mask replay; the default below 10 % density) or the transposing tiled fill -- both forced here
+        for fill in ("replay", "tiled", None):
+            if fill:
+                os.environ["SS_CSR_FILL"] = fill
+            try:
+                h = C.c_void_p()
+                check(ss.lib().ss_featurize_csr(ctx.h, d.h, alpha, int(weighted), C.byref(h)))
+            finally:
+                os.environ.pop("SS_CSR_FILL", None)
+            r, c, nnz, hv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+            check(ss.lib().ss_csr_info(h, C.byref(r), C.byref(c), C.byref(nnz), C.byref(hv)))
+            rp = np.empty(rows + 1, np.int32)
+            ci = np.empty(max(nnz.value, 1), np.int32)
+            va = np.empty(max(nnz.value, 1), np.float64)
+            check(ss.lib().ss_csr_download(ctx.h, h, rp.ctypes.data, ci.ctypes.data, va.ctypes.data if hv.value else None))
+            ss.lib().ss_csr_destroy(h)
+            assert nnz.value == len(wr) and bool(hv.value) == weighted
+            assert np.array_equal(rp, np.concatenate(([0], np.cumsum(np.bincount(wr, minlength=rows)))).astype(np.int32))
+            assert np.array_equal(ci[:nnz.value], wc.astype(np.int32))
+            if weighted:
+                assert np.array_equal(va[:nnz.value], want[wr, wc])
 
 
 @pytest.mark.parametrize("ns,nf,nt", [(1, 1, 1), (13, 13, 5), (401, 401, 664), (1500, 700, 129)])
@@ -485,6 +492,38 @@ def test_gemm_k_blocking_switch(ss, o):
     got = R.to_host()
     assert relerr(got, want) < RTOL
     assert np.array_equal(got == -99, want == -99)
+
+
+@pytest.mark.parametrize("M,N,K", [(600, 1250, 130), (1650, 1660, 100), (1790, 1900, 70), (2400, 1000, 4000)])
+@pytest.mark.parametrize("op", ["N", "T"])
+def test_gemm_partial_wave_in_row_bands_is_bit_identical(ss, M, N, K, op):
+    """The tiles of a partial last wave run as 2 or 4 row bands (csrc/ss_gemm.cu, Unit): 50 tiles -> halves, 169 = 148 +
+    21 -> quarters, 210 = 148 + 62 -> halves, 152 = 148 + 4 at a long K.  Every entry accumulates the same DMMA sequence,
+    so the result must equal the whole-tile launch (SS_GEMM_TAIL_SPLIT=0) bit for bit, epilogues included."""
+    from simspread_b200._lib import SS_OP_N, SS_OP_T, check
+    rng = np.random.default_rng(M + N + K)
+    ctx = ss.Context.default()
+    A, B = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+    dA = ss.DMat.from_host(ctx, A if op == "N" else A.T)
+    dB = ss.DMat.from_host(ctx, B)
+    dd = ss.DIVec.from_host(ctx, rng.integers(0, 4, size=M).astype(np.int32))
+    df = ss.DIVec.from_host(ctx, rng.integers(0, 2, size=N).astype(np.int32))
+    o_ = SS_OP_N if op == "N" else SS_OP_T
+    res = {}
+    for split in ("0", "2", "4"):
+        os.environ["SS_GEMM_TAIL_SPLIT"] = split
+        try:
+            dC, dE = ss.DMat(ctx, M, N), ss.DMat(ctx, M, N)
+            check(ss.lib().ss_gemm_f64(ctx.h, o_, dA.h, dB.h, dC.h, None, None))
+            check(ss.lib().ss_gemm_f64(ctx.h, o_, dA.h, dB.h, dE.h, dd.h, df.h))
+            res[split] = (dC.to_host(), dE.to_host())
+        finally:
+            os.environ.pop("SS_GEMM_TAIL_SPLIT", None)
+    want = A @ B
+    bound = np.abs(A) @ np.abs(B)
+    assert np.max(np.abs(res["0"][0] - want) / bound) < 1e-13
+    for split in ("2", "4"):
+        assert np.array_equal(res[split][0], res["0"][0]) and np.array_equal(res[split][1], res["0"][1])
 
 
 def test_empty_and_degenerate_inputs(ss, o):
