@@ -8,13 +8,13 @@
 //   1. csr_count_kernel: lanes along ROWS (every load is a 256-byte run of one column, as in the degree kernel), a
 //      warp owns 32 rows x one segment of columns.  A lane thresholds 32 columns of its row into one word of the
 //      keep-mask (bit j = column 32 w + j kept) straight from registers -- no shared-memory transpose, no barriers --
-//      and counts its row's edges of the segment.  The mask is stored word-major (mask[w][row]: coalesced).
+//      and counts its row's edges of the segment.  The words of a warp are transposed through shared memory and the
+//      mask is stored row-major.
 //   2. scan_*: device-wide exclusive scan of the (row, segment) counts in row-major order, which IS the CSR order:
-//      it yields the start of every (row, segment) run and, at segment 0, row_ptr.
-//   3. csr_fill_kernel (results below 10 % density): the same (32 rows x segment) decomposition replays the mask --
-//      1/64 of the bytes of S -- and writes col_idx / values of its run; for weighted graphs only the 32-byte sectors
-//      of the kept similarities are read again.  Up to four set bits are taken per round so that their gathers are in
-//      flight together.  Denser results keep the transposing tiled fill (csr_tiled_fill_kernel): lanes along rows for
+//      at segment 0 of every row it yields row_ptr.
+//   3. csr_fill_kernel (results below 10 % density): one warp per row replays the mask -- 1/64 of the bytes of S --
+//      and writes col_idx / values of the row with contiguous stores; for weighted graphs only the 32-byte sectors of
+//      the kept similarities are read again, up to four per lane in flight.  Denser results keep the transposing tiled fill (csr_tiled_fill_kernel): lanes along rows for
 //      the loads, a padded shared-memory tile, lanes along columns with __ballot_sync + popc for the compaction.
 #include <stdlib.h>
 #include <string.h>
@@ -33,15 +33,26 @@ __device__ __forceinline__ bool keep_edge(double x, double alpha, bool weighted)
 }
 
 // ---- 1. count + keep-mask ----------------------------------------------------------------------------------------
-// grid.x covers the 32-row blocks (8 per thread block, one per warp), grid.y the column segments of seg_words words.
+// grid.x covers the 32-row blocks (8 per thread block, one per warp), grid.y the column segments of seg_words words
+// (4, 8, 16 or 32).  The words of a warp (32 rows x seg_words) are transposed through shared memory so that the mask
+// is stored row-major (mask[row][word], seg_words * 4 contiguous bytes per row): the fill walks a row with lanes along
+// its words.
 constexpr int CNT_BATCH = 16;  // independent 8-byte loads per lane in flight (two batches make one mask word)
 
+//
+// Measured and dropped: queueing the kept similarities of a weighted graph from the registers of this kernel (shared-
+// memory queues copied to staging slots, read back by the fill as contiguous runs instead of one 32-byte sector of S
+// per edge).  The fill drops from 2.0 to 0.6 ms at 4 % density, but the 32 conditional queue stores per word cost the
+// count pass 1.2 ms at any density (and placed next to the compares they make ptxas sink every load to its use: 8.9
+// ms), so it only pays above ~3.5 % density -- where predict switches to the dense chain anyway.
 __global__ void __launch_bounds__(CSR_TPB, 3)
     csr_count_kernel(const double* __restrict__ S, int64_t rows, int64_t cols, int64_t ld, double alpha, int weighted,
-                     int64_t mask_words, int seg_words, int nseg, int64_t rows_pad, uint32_t* __restrict__ keep_mask,
+                     int64_t mask_words, int seg_words, int nseg, uint32_t* __restrict__ keep_mask,
                      int32_t* __restrict__ seg_count) {
-    const int lane = threadIdx.x & 31;
-    const int64_t rb = int64_t(blockIdx.x) * (CSR_TPB / 32) + (threadIdx.x >> 5);
+    extern __shared__ uint32_t csr_tr[];  // mask words of the block: [warp][lane][seg_words + 1]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* tr = csr_tr + size_t(warp) * 32 * (seg_words + 1);
+    const int64_t rb = int64_t(blockIdx.x) * (CSR_TPB / 32) + warp;
     const int64_t row = rb * 32 + lane;
     if (rb * 32 >= rows) return;  // warp-uniform
     const bool w = weighted != 0;
@@ -72,10 +83,18 @@ __global__ void __launch_bounds__(CSR_TPB, 3)
             }
         }
         if (!live) bits = 0;
-        keep_mask[wd * rows_pad + rb * 32 + lane] = bits;
+        tr[lane * (seg_words + 1) + int(wd - w0)] = bits;
         cnt += __popc(bits);
     }
     if (live) seg_count[row * nseg + seg] = cnt;
+    __syncwarp();
+    // row-major store of the mask: one instruction covers 32 / seg_words rows x seg_words words
+    const int nw = int(w1 - w0);
+    const int j = lane % seg_words, r_in = lane / seg_words, r_step = 32 / seg_words;
+    for (int rr = r_in; rr < 32; rr += r_step) {
+        const int64_t r = rb * 32 + rr;
+        if (r < rows && j < nw) keep_mask[r * mask_words + w0 + j] = tr[rr * (seg_words + 1) + j];
+    }
 }
 
 // ---- 2. device-wide exclusive scan of int32 counts (int64 running sums; overflow of the int32 result reported) ------
@@ -169,34 +188,42 @@ __global__ void __launch_bounds__(SCAN_TPB)
 }
 
 // ---- 3a. fill by mask replay (sparse results) -------------------------------------------------------------------
-constexpr int FILL_TAKE = 4;  // set bits taken per round: their gathers are issued together
+// One warp per row; lane l takes mask word l, l + 32, ...; a warp prefix over the popcounts gives every kept entry its
+// slot, so col_idx / values of a row are written in ascending column order and the stores of a warp are contiguous.
+// Up to four set bits of a word are taken per round so that their gathers are in flight together (the loads are
+// unconditional on a valid dummy column: a predicated load would make every load blocking).
+constexpr int FILL_TAKE = 4;
 
 __global__ void __launch_bounds__(CSR_TPB)
     csr_fill_kernel(const double* __restrict__ S, int64_t rows, int64_t ld, const uint32_t* __restrict__ keep_mask,
-                    int64_t mask_words, int seg_words, int nseg, int64_t rows_pad, const int32_t* __restrict__ offs,
-                    int32_t* __restrict__ col_idx, double* __restrict__ values) {
+                    int64_t mask_words, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx,
+                    double* __restrict__ values) {
     const int lane = threadIdx.x & 31;
-    const int64_t rb = int64_t(blockIdx.x) * (CSR_TPB / 32) + (threadIdx.x >> 5);
-    const int64_t row = rb * 32 + lane;
-    if (rb * 32 >= rows) return;  // warp-uniform
-    const bool live = row < rows;
-    const double* base = S + (live ? row : rows - 1);
-    const int seg = blockIdx.y;
-    const int64_t w0 = int64_t(seg) * seg_words, w1 = min(mask_words, w0 + seg_words);
-    int32_t pos = live ? offs[row * nseg + seg] : 0;
-    uint32_t next = keep_mask[w0 * rows_pad + rb * 32 + lane];
-    for (int64_t wd = w0; wd < w1; ++wd) {
-        uint32_t bits = next;  // rows past the end hold empty words
-        if (wd + 1 < w1) next = keep_mask[(wd + 1) * rows_pad + rb * 32 + lane];
-        const int64_t c0 = wd << 5;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const uint32_t* m = keep_mask + row * mask_words;
+    const double* base = S + row;
+    int32_t run = row_ptr[row];
+    for (int64_t wb = 0; wb < mask_words; wb += 32) {
+        const int64_t wd = wb + lane;
+        uint32_t bits = wd < mask_words ? __ldg(m + wd) : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        int32_t pos = run + incl - cnt;
+        const int32_t c0 = int32_t(wd << 5);
         while (bits) {
             int32_t c[FILL_TAKE];
             bool ok[FILL_TAKE];
 #pragma unroll
             for (int u = 0; u < FILL_TAKE; ++u) {
                 ok[u] = bits != 0;
-                c[u] = int32_t(c0) + (ok[u] ? __ffs(bits) - 1 : 0);  // column c0 exists whenever the word does
-                bits &= bits - 1;                                     // 0 stays 0
+                c[u] = c0 + (ok[u] ? __ffs(bits) - 1 : 0);  // column c0 exists whenever the word has a bit
+                bits &= bits - 1;                            // 0 stays 0
             }
             if (values) {
                 double v[FILL_TAKE];
@@ -211,6 +238,7 @@ __global__ void __launch_bounds__(CSR_TPB)
                 if (ok[u]) col_idx[pos + u] = c[u];
             pos += int(ok[0]) + int(ok[1]) + int(ok[2]) + int(ok[3]);
         }
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -294,28 +322,30 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
     // decomposition: 32-row blocks x column segments of seg_words mask words; short segments for small matrices so
     // that the grid still covers the GPU, at most 32 words (1024 columns) per segment
     const int64_t mask_words = ceil_div(cols, 32);
-    const int64_t row_blocks = ceil_div(rows, 32), rows_pad = row_blocks * 32;
+    const int64_t row_blocks = ceil_div(rows, 32);
     int seg_words = 32;
-    while (seg_words > 4 && row_blocks * ceil_div(mask_words, seg_words) < 8 * 64 * int64_t(ctx->sm_count)) seg_words >>= 1;
-    while (ceil_div(mask_words, seg_words) > 65535) seg_words <<= 1;  // grid.y limit (matrices wider than 8 M columns)
+    while (seg_words > 4 && row_blocks * ceil_div(mask_words, seg_words) < 8 * 64 * int64_t(ctx->sm_count) &&
+           ceil_div(mask_words, seg_words / 2) <= 65535)
+        seg_words >>= 1;
+    SS_REQUIRE(ceil_div(mask_words, seg_words) <= 65535, "featurize_csr: more than 67 M columns are not supported");
     const int nseg = int(ceil_div(mask_words, seg_words));
     const int64_t n = rows * nseg;  // (row, segment) counts, row-major = CSR order
     const int64_t nb = ceil_div(n, SCAN_TILE);
     void* p;
-    if ((status = scratch_get(ctx, 8, size_t(n) * 4 * 2 + size_t(nb) * 8 + 64, &p)) != SS_OK) return fail(status);
+    if ((status = scratch_get(ctx, 8, size_t(n) * 4 + size_t(nb) * 8 + 64, &p)) != SS_OK) return fail(status);
     int32_t* seg_count = static_cast<int32_t*>(p);
-    int32_t* offs = seg_count + n;
-    long long* bsum = reinterpret_cast<long long*>(reinterpret_cast<char*>(p) + ((size_t(n) * 8 + 15) & ~size_t(15)));
+    long long* bsum = reinterpret_cast<long long*>(reinterpret_cast<char*>(p) + ((size_t(n) * 4 + 15) & ~size_t(15)));
     int32_t* overflow = reinterpret_cast<int32_t*>(bsum + nb);
     void* mp;
-    if ((status = scratch_get(ctx, 22, size_t(rows_pad) * size_t(mask_words) * 4, &mp)) != SS_OK) return fail(status);
+    if ((status = scratch_get(ctx, 22, size_t(rows) * size_t(mask_words) * 4, &mp)) != SS_OK) return fail(status);
     uint32_t* keep_mask = static_cast<uint32_t*>(mp);
     const dim3 grid(unsigned(ceil_div(row_blocks, CSR_TPB / 32)), unsigned(nseg));
-    csr_count_kernel<<<grid, CSR_TPB, 0, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0, mask_words, seg_words,
-                                                         nseg, rows_pad, keep_mask, seg_count);
+    const size_t tr_bytes = size_t(CSR_TPB / 32) * 32 * (seg_words + 1) * 4;
+    csr_count_kernel<<<grid, CSR_TPB, tr_bytes, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0, mask_words, seg_words,
+                                                                nseg, keep_mask, seg_count);
     scan_block_sums_kernel<<<unsigned(nb), SCAN_TPB, 0, ctx->stream>>>(seg_count, n, bsum);
     scan_block_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(bsum, nb, c->row_ptr + rows, overflow);
-    scan_apply_kernel<<<unsigned(nb), SCAN_TPB, 0, ctx->stream>>>(seg_count, n, bsum, nseg, offs, c->row_ptr);
+    scan_apply_kernel<<<unsigned(nb), SCAN_TPB, 0, ctx->stream>>>(seg_count, n, bsum, nseg, nullptr, c->row_ptr);
     ctx->launches += 4;
     int32_t h[2] = {0, 0};
     cudaMemcpyAsync(&h[0], c->row_ptr + rows, 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -347,8 +377,8 @@ int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted,
             if (!strcmp(env, "replay")) replay = true;
         }
         if (replay) {
-            csr_fill_kernel<<<grid, CSR_TPB, 0, ctx->stream>>>(S->d, rows, S->ld, keep_mask, mask_words, seg_words, nseg, rows_pad,
-                                                                offs, c->col_idx, c->values);
+            csr_fill_kernel<<<unsigned(ceil_div(rows * 32, CSR_TPB)), CSR_TPB, 0, ctx->stream>>>(S->d, rows, S->ld, keep_mask, mask_words,
+                                                                                             c->row_ptr, c->col_idx, c->values);
         } else {
             csr_tiled_fill_kernel<<<unsigned(row_blocks), CSR_TPB, 0, ctx->stream>>>(S->d, rows, cols, S->ld, alpha, weighted ? 1 : 0,
                                                                                      c->row_ptr, c->col_idx, c->values);

@@ -25,7 +25,7 @@ constexpr int STAGES = 6;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int WARPS_N = 4;            // warp grid 2 (m) x 4 (n)
 constexpr int WM = 64, WN = 32;       // warp tile
-constexpr int MT = WM / 8, NT = WN / 8;
+constexpr int NT = WN / 8;
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
 constexpr int A_BYTES = BM * BK * 8;  // 16 KB
 constexpr int B_BYTES = BN * BK * 8;  // 16 KB
@@ -102,21 +102,20 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles
 // grid with a shorter warp tile; every output element still accumulates k = 0 .. K-1 in the same DMMA sequence, so
 // the result does not depend on the split (bit-identical to whole tiles).
 struct Unit {
-    int tile, band, split;
+    int tm, tn, band, split;
 };
-__device__ __forceinline__ Unit unit_of(int u, int full_tiles, int tail_split) {
-    if (u < full_tiles) return {u, 0, 1};
-    const int v = u - full_tiles;
-    return {full_tiles + v / tail_split, v % tail_split, tail_split};
-}
 
 struct GemmParams {
     double* C;
     int64_t ldc;
     int M, N, K;
     int tiles_m, tiles_n;
-    int full_tiles;           // tiles [0, full_tiles) are whole waves of 128 x 128 tiles
+    int full_tiles;           // units [0, full_tiles) are whole 128 x 128 tiles (whole waves of them)
     int tail_split;           // the remaining tiles are cut into 1 / 2 / 4 row bands, one band per work unit
+    int reg_rows;             // row tiles enumerated by tile_coord: tiles_m, or tiles_m - 1 when the last row tile is
+    int reg_tiles;            //   short (few valid rows); reg_tiles = reg_rows * tiles_n
+    int short_bands;          // bands that cover the valid rows of a short last row tile (0: no such tiles); those
+    int total_units;          //   tiles come last in the unit list, short_bands units each
     const int32_t* row_div;   // optional: C[m,:] = acc / row_div[m] (0 when row_div[m] == 0)
     const int32_t* col_flag;  // optional: C[:,n] = -99 when col_flag[n] == 0
     int accumulate;           // C += result
@@ -125,6 +124,23 @@ struct GemmParams {
     int nmirror;              // fused all-gather: every C element is also stored to these peer-GPU
     double* mirror[7];        // copies of C (same ld), over NVLink P2P, straight from the epilogue
 };
+
+// Unit list: whole tiles [0, full_tiles), then the bands of the remaining regular tiles, then the bands of the short
+// tiles of the last row tile (only the bands that hold valid rows).
+__device__ __forceinline__ Unit unit_of(int u, const GemmParams& p) {
+    if (u < p.full_tiles) {
+        const TileCoord tc = tile_coord(u, p.reg_rows, p.tiles_n);
+        return {tc.tm, tc.tn, 0, 1};
+    }
+    const int v = u - p.full_tiles;
+    const int nreg = (p.reg_tiles - p.full_tiles) * p.tail_split;
+    if (v < nreg) {
+        const TileCoord tc = tile_coord(p.full_tiles + v / p.tail_split, p.reg_rows, p.tiles_n);
+        return {tc.tm, tc.tn, v % p.tail_split, p.tail_split};
+    }
+    const int w = v - nreg;
+    return {p.tiles_m - 1, w / p.short_bands, w % p.short_bands, p.tail_split};
+}
 
 __device__ __forceinline__ void store1(const GemmParams& p, int64_t off, double v) {
     p.C[off] = v;
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int kblocks = (p.K + BK - 1) / BK;
-    const int total_units = p.full_tiles + (p.tiles_m * p.tiles_n - p.full_tiles) * p.tail_split;
+    const int total_units = p.total_units;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -291,8 +307,8 @@ __global__ void __launch_bounds__(THREADS, 1)
             uint32_t phase = 0;
             int checkpoint = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-                const Unit un = unit_of(u, p.full_tiles, p.tail_split);
-                const TileCoord tc = tile_coord(un.tile, p.tiles_m, p.tiles_n);
+                const Unit un = unit_of(u, p);
+                const Unit& tc = un;
                 const int n0 = tc.tn * BN;
                 // rows of A this unit needs: the whole tile, or one band of it (multiples of 16 rows)
                 const int band_rows = BM / un.split;
@@ -359,9 +375,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const Unit un = unit_of(u, p.full_tiles, p.tail_split);
-        const TileCoord tc = tile_coord(un.tile, p.tiles_m, p.tiles_n);
-        const int m0 = tc.tm * BM, n0 = tc.tn * BN;
+        const Unit un = unit_of(u, p);
+        const int m0 = un.tm * BM, n0 = un.tn * BN;
         if (un.split == 1)
             consume_unit<A_MMAJOR, 8>(p, smem_base, bar_base, m0, n0, 0, kblocks, warp, lane, stage, phase);
         else if (un.split == 2)
@@ -454,24 +469,52 @@ static int32_t launch_gemm_f64_one(ss_ctx* ctx, int opA, const double* A, int64_
         if (reinterpret_cast<uintptr_t>(mirrors[i]) & 15) p.cvec = 0;
     const int64_t total = int64_t(p.tiles_m) * p.tiles_n;
     SS_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
-    // partial last wave: cut its tiles into 2 or 4 row bands when that fills more SMs (see Unit); SS_GEMM_TAIL_SPLIT=0
-    // keeps whole tiles (A/B measurements)
+    // Partial last wave: cut the trailing tiles into 2 or 4 row bands when that shortens the launch (see Unit).  The
+    // candidates are the tiles of the partial wave alone, or together with the last whole wave; a band costs a little
+    // more per row than a whole tile (the B slab is re-read per band), hence the 4 % / 8 % handicap.  With bands a
+    // last row tile that holds few valid rows (M = 5000: 8 of 128) only gets the bands that hold rows.
+    // SS_GEMM_TAIL_SPLIT=0 keeps whole tiles, =2 allows halves only (A/B measurements, tests).
     const int64_t sms = ctx->sm_count;
-    const int64_t rem = total % sms;
-    int split = 1;
+    int split = 1, short_bands = 0;
+    int64_t full = total, reg_rows = p.tiles_m;
     {
         const char* e = getenv("SS_GEMM_TAIL_SPLIT");
         const int allow = e ? atoi(e) : 4;
-        if (rem > 0 && K >= 64) {
-            if (allow >= 4 && rem * 4 <= sms) split = 4;
-            else if (allow >= 2 && rem * 2 <= sms) split = 2;
+        double best = double(ceil_div(total, sms));
+        const int64_t valid_last = M - int64_t(p.tiles_m - 1) * BM;  // rows of the last row tile
+        if (K >= 64) {
+            for (int s = 2; s <= allow && s <= 4; s *= 2) {
+                const int64_t band_rows = BM / s;
+                const int64_t sb = ceil_div(valid_last, band_rows) < s ? ceil_div(valid_last, band_rows) : 0;  // short?
+                const int64_t rr = sb ? p.tiles_m - 1 : p.tiles_m;
+                const int64_t reg = rr * p.tiles_n, shorts = sb ? p.tiles_n : 0;
+                const int64_t rem = reg % sms;
+                for (int j = 0; j <= 1; ++j) {
+                    const int64_t f = reg - rem - j * sms;
+                    if (f < 0 || (reg - f) * s + shorts * sb == 0) continue;
+                    const double cost = double(f / sms) +
+                                        double(ceil_div((reg - f) * s + shorts * sb, sms)) / s * (s == 2 ? 1.04 : 1.08);
+                    if (cost < best * 0.98) {
+                        best = cost;
+                        split = s;
+                        full = f;
+                        short_bands = int(sb);
+                        reg_rows = rr;
+                    }
+                }
+            }
         }
     }
     p.tail_split = split;
-    p.full_tiles = int(split > 1 ? total - rem : total);
-    const int64_t units = p.full_tiles + (total - p.full_tiles) * split;
+    p.full_tiles = int(full);
+    p.reg_rows = int(reg_rows);
+    p.reg_tiles = int(reg_rows * p.tiles_n);
+    p.short_bands = short_bands;
+    const int64_t units = full + (p.reg_tiles - full) * split + (short_bands ? int64_t(p.tiles_n) * short_bands : 0);
+    SS_REQUIRE(units < (1ll << 31), "gemm: too many work units");
+    p.total_units = int(units);
     const int grid = int(units < sms ? units : sms);
-    if (total > grid) {  // more than one wave: keep the waves in lockstep for L2 reuse
+    if (units > grid) {  // more than one wave: keep the waves in lockstep for L2 reuse
         if (!ctx->tile_counter) SS_CHECK_CUDA(cudaMalloc(&ctx->tile_counter, 4096));
         SS_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, size_t(grid) * 4, ctx->stream));
         p.sync_prog = ctx->tile_counter;

@@ -186,28 +186,74 @@ def test_row_bands_reproduce_the_tile(a_mmajor, split):
     assert np.array_equal(C, A @ B) and np.all(writes == 1)
 
 
-def test_unit_enumeration_covers_every_tile_once():
-    """Host-side choice of the split (launch_gemm_f64_one) + unit_of: whole waves as tiles, the rest as bands."""
+def choose_split(M, N, sms=148, allow=4):
+    """launch_gemm_f64_one's choice of the unit list: (full_tiles, split, reg_rows, short_bands, cost)."""
+    tiles_m, tiles_n = -(-M // 128), -(-N // 128)
+    total = tiles_m * tiles_n
+    best, split, full, reg_rows, short_bands = float(-(-total // sms)), 1, total, tiles_m, 0
+    valid_last = M - (tiles_m - 1) * 128
+    s = 2
+    while s <= allow and s <= 4:
+        band_rows = 128 // s
+        sb = -(-valid_last // band_rows)
+        sb = sb if sb < s else 0
+        rr = tiles_m - 1 if sb else tiles_m
+        reg, shorts = rr * tiles_n, (tiles_n if sb else 0)
+        rem = reg % sms
+        for j in (0, 1):
+            f = reg - rem - j * sms
+            if f < 0 or (reg - f) * s + shorts * sb == 0:
+                continue
+            cost = f // sms + (-(-((reg - f) * s + shorts * sb) // sms)) / s * (1.04 if s == 2 else 1.08)
+            if cost < best * 0.98:
+                best, split, full, reg_rows, short_bands = cost, s, f, rr, sb
+        s *= 2
+    return full, split, reg_rows, short_bands, best
+
+
+def coord(tile, tiles_m, tiles_n, GROUP_M=16):
+    gs = GROUP_M * tiles_n
+    gid = tile // gs
+    first = gid * GROUP_M
+    gm = min(tiles_m - first, GROUP_M)
+    r = tile - gid * gs
+    return first + r % gm, r // gm
+
+
+def test_unit_enumeration_covers_every_valid_row_once():
+    """Host-side choice of the split + unit_of: whole waves as tiles, the trailing tiles as row bands, a short last row
+    tile as the bands that hold rows.  Every (row, column tile) with a valid row is computed by exactly one unit."""
     sms = 148
-    for total in [1, 6, 37, 38, 74, 75, 147, 148, 149, 169, 210, 222, 640, 148 * 7 + 36]:
-        rem = total % sms
-        split = 4 if (rem and rem * 4 <= sms) else 2 if (rem and rem * 2 <= sms) else 1
-        full = total - rem if split > 1 else total
-        units = full + (total - full) * split
-        seen = {}
+    shapes = [(1, 1), (600, 1250), (1650, 1660), (1790, 1900), (2400, 1000), (2040, 2048), (5000, 2000), (5000, 5000),
+              (2000, 2000), (12500, 50000), (100000, 50000), (130, 130), (128 * 148, 128), (128 * 37 + 1, 128 * 4)]
+    for M, N in shapes:
+        tiles_m, tiles_n = -(-M // 128), -(-N // 128)
+        full, split, reg_rows, sb, cost = choose_split(M, N, sms)
+        reg_tiles = reg_rows * tiles_n
+        units = full + (reg_tiles - full) * split + (tiles_n * sb if sb else 0)
+        assert full % sms == 0 or split == 1
+        cover = np.zeros((tiles_m * 128, tiles_n), dtype=int)
         for u in range(units):
             if u < full:
-                t, band, sp = u, 0, 1
+                tm, tn = coord(u, reg_rows, tiles_n)
+                band, sp = 0, 1
             else:
                 v = u - full
-                t, band, sp = full + v // split, v % split, split
-            seen.setdefault(t, []).append((band, sp))
-        assert sorted(seen) == list(range(total))
-        for t, parts in seen.items():
-            sp = parts[0][1]
-            assert sorted(b for b, _ in parts) == list(range(sp))
-        if split > 1:
-            assert units - full <= sms  # the bands of the partial wave fit one round of the grid
+                nreg = (reg_tiles - full) * split
+                if v < nreg:
+                    tm, tn = coord(full + v // split, reg_rows, tiles_n)
+                    band, sp = v % split, split
+                else:
+                    w = v - nreg
+                    tm, tn, band, sp = tiles_m - 1, w // sb, w % sb, split
+            rows = 128 // sp
+            cover[tm * 128 + band * rows: tm * 128 + (band + 1) * rows, tn] += 1
+        assert np.all(cover[:M] == 1), (M, N)
+        assert cost <= -(-(tiles_m * tiles_n) // sms)
+    assert choose_split(5000, 2000)[:4] == (592, 4, 39, 1)   # C3: 624 regular tiles + 16 tiles with 8 valid rows
+    assert choose_split(2000, 2000)[1] == 4                   # 1 wave + 108 tiles -> everything in quarter tiles
+    assert choose_split(100000, 50000)[1] == 1                # C4: 2 066 waves stay whole tiles
+    assert choose_split(12500, 50000)[1] == 1
 
 
 def test_tile_rasterisation_is_a_bijection():

@@ -63,6 +63,7 @@ def test_c4_full_size_chain_properties(env):
     bY[7, :] = 0.0      # a target nobody has: clean! must flag its column
     bXs[:, 11] = 0.0    # a source without features (it still has targets)
     bXs[13, :] = 0.0    # a feature nobody has: kf = 0 -> its row of T is 0, not NaN
+    torch.cuda.synchronize()  # the library has its own stream: torch's writes must have landed before it reads them
     mXq, mXs = ss.DMat.wrap(ctx, bXq.data_ptr(), nq, nf, ldq), ss.DMat.wrap(ctx, bXs.data_ptr(), ns, nf, lds)
     mY, mR = ss.DMat.wrap(ctx, bY.data_ptr(), ns, nt, ldy), ss.DMat.wrap(ctx, bR.data_ptr(), nq, nt, ldr)
     kt = ss.DIVec(ctx, nt)
@@ -153,6 +154,7 @@ def test_c4_full_size_featurize_degrees_csr(env):
     bS[3, 5] = float("nan")   # NaN >= alpha is false -> 0
     bS[4, 6] = alpha          # inclusive threshold
     bX, _ = colmajor(torch, n, m, dev)
+    torch.cuda.synchronize()  # torch's fills (other stream) before the library reads them
     mS, mX = ss.DMat.wrap(ctx, bS.data_ptr(), n, m, ld), ss.DMat.wrap(ctx, bX.data_ptr(), n, m, ld)
     check(L.ss_featurize(ctx.h, mS.h, alpha, 1, mX.h))
     torch.cuda.synchronize()
@@ -221,6 +223,7 @@ def test_full_size_ranking_metric_properties(env):
     bR, ldr = colmajor(torch, rows, cols, dev)
     fill(torch, bR, rows, 31, "uniform6")
     mR = ss.DMat.wrap(ctx, bR.data_ptr(), rows, cols, ldr)
+    torch.cuda.synchronize()
     idx = ss.DIVec(ctx, Ltop * rows)
     check(L.ss_topl_rows(ctx.h, mR.h, Ltop, idx.h, None))
     ih = torch.from_numpy(idx.to_host().reshape(rows, Ltop).astype(np.int64)).to(dev)
@@ -263,6 +266,7 @@ def test_c5_full_size_graph_user_slice_against_scipy(env, degrees, weighted):
     users = 20_000 if exact else 2_000  # a slice of the users; U is that of the whole graph
     idx = torch.full((ns, topl), -2, dtype=torch.int32, device=dev)
     val = torch.zeros((ns, topl), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()  # torch's fills must not land after the library (own stream) has written its results
     vi, vm = C.c_void_p(), C.c_void_p()
     check(L.ss_ivec_wrap(ctx.h, C.c_void_p(idx.data_ptr()), ns * topl, C.byref(vi)))
     check(L.ss_mat_wrap(ctx.h, C.c_void_p(val.data_ptr()), topl, ns, topl, C.byref(vm)))

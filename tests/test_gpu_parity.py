@@ -494,11 +494,13 @@ def test_gemm_k_blocking_switch(ss, o):
     assert np.array_equal(got == -99, want == -99)
 
 
-@pytest.mark.parametrize("M,N,K", [(600, 1250, 130), (1650, 1660, 100), (1790, 1900, 70), (2400, 1000, 4000)])
+@pytest.mark.parametrize("M,N,K", [(600, 1250, 130), (1650, 1660, 100), (1790, 1900, 70), (2400, 1000, 4000), (2040, 2048, 80),
+                                   (1928, 1300, 90), (424, 700, 300)])
 @pytest.mark.parametrize("op", ["N", "T"])
 def test_gemm_partial_wave_in_row_bands_is_bit_identical(ss, M, N, K, op):
     """The tiles of a partial last wave run as 2 or 4 row bands (csrc/ss_gemm.cu, Unit): 50 tiles -> halves, 169 = 148 +
-    21 -> quarters, 210 = 148 + 62 -> halves, 152 = 148 + 4 at a long K.  Every entry accumulates the same DMMA sequence,
+    21 -> quarters, 210 = 148 + 62 -> halves, 152 = 148 + 4 at a long K, 256 = 148 + 108 -> all tiles in quarters (several
+    bands per CTA); 1928 and 424 rows end in a row tile with 8 / 40 valid rows, which gets one / two quarter bands only.  Every entry accumulates the same DMMA sequence,
     so the result must equal the whole-tile launch (SS_GEMM_TAIL_SPLIT=0) bit for bit, epilogues included."""
     from simspread_b200._lib import SS_OP_N, SS_OP_T, check
     rng = np.random.default_rng(M + N + K)

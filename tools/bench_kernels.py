@@ -80,11 +80,16 @@ def csr(alpha, weighted):
 
 
 nnz = csr(0.96, 1)
-report("featurize_csr (count + mask, scan, mask-replay fill; weighted, alpha=0.96)", n, "elements", 8 * n + 12 * nnz + 4 * rows,
+report("featurize_csr (count + mask with lanes along rows, device scan, segment replay fill; weighted, alpha=0.96)", n, "elements",
+       8 * n + 12 * nnz + 4 * rows,
        lambda: csr(0.96, 1), f"S read ONCE: 8 B per element + 12 B per kept edge ({nnz} edges, {nnz / n:.1%} dense); the fill pass "
-       "replays the keep-mask of the count pass and touches only the sectors of kept entries; includes cudaMalloc of the CSR")
+       "replays the keep-mask of the count pass and touches only the sectors of kept entries; includes the host sync for nnz "
+       "and cudaMallocAsync of the CSR arrays")
+nnzb = csr(0.96, 0)
+report("featurize_csr (same, binary graph: no values)", n, "elements", 8 * n + 4 * nnzb + 4 * rows, lambda: csr(0.96, 0),
+       "the fill reads the mask only")
 os.environ["SS_CSR_FILL"] = "tiled"
-report("featurize_csr, round-1 form (count, scan, tiled fill; weighted, alpha=0.96)", n, "elements", 8 * n + 12 * nnz + 4 * rows,
+report("featurize_csr with the tiled fill forced (weighted, alpha=0.96)", n, "elements", 8 * n + 12 * nnz + 4 * rows,
        lambda: csr(0.96, 1), "same algorithmic bytes, S read twice")
 del os.environ["SS_CSR_FILL"]
 nnz9 = csr(0.8, 1)
@@ -123,5 +128,28 @@ report("auroc_auprc (radix sort + curve scan), M = 1e8", M, "scores", 9 * M * (2
        lambda: check(L.ss_auroc_auprc(ctx.h, C.c_void_p(lb.data_ptr()), C.c_void_p(sc.data_ptr()), M, res)),
        "9 B per score x (key build + histogram + <= 8 passes x (upsweep read, downsweep read + write))")
 out["auroc_auprc_value"] = [res[0], res[1]]
+del sc, lb
+
+# mid-size chain products (BASELINE config 3: 5000 x 2000 x 5000 -> 640 tiles = 4 waves + 48 tiles): the partial wave
+# as whole tiles (SS_GEMM_TAIL_SPLIT=0) and as row bands (default); results are bit-identical (tests)
+from simspread_b200._lib import SS_OP_N, SS_OP_T
+out["gemm_mid_size"] = []
+for (M_, N_, K_) in [(5000, 2000, 5000), (5000, 5000, 5000), (2000, 2000, 20000), (12500, 50000, 2500)]:
+    bA, mA = colmajor(M_, K_, uni)
+    bAt, mAt = colmajor(K_, M_, uni)
+    bB, mB = colmajor(K_, N_, uni)
+    bC, mC = colmajor(M_, N_, lambda b: b.zero_())
+    for op, a in (("N", mA), ("T", mAt)):
+        rec = {"M": M_, "N": N_, "K": K_, "opA": op, "tiles": ((M_ + 127) // 128) * ((N_ + 127) // 128)}
+        for name, env in (("whole_tiles", "0"), ("row_bands", None)):
+            if env is not None:
+                os.environ["SS_GEMM_TAIL_SPLIT"] = env
+            best, med = timed(lambda: check(L.ss_gemm_f64(ctx.h, SS_OP_N if op == "N" else SS_OP_T, a.h, mB.h, mC.h, None, None)))
+            os.environ.pop("SS_GEMM_TAIL_SPLIT", None)
+            rec[name] = {"ms_median": med, "ms_best": best, "tflops": 2.0 * M_ * N_ * K_ / (med * 1e-3) / 1e12}
+        out["gemm_mid_size"].append(rec)
+        print(json.dumps(rec), flush=True)
+    del bA, mA, bAt, mAt, bB, mB, bC, mC
+
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/kernels.json", "w"), indent=1)
