@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(TOPL_TPB)
 // the stable descending order of `sortperm(row; rev=true)`.
 // ------------------------------------------------------------------------------------------------
 constexpr int WT_ROWS = 32;
-constexpr int WT_COLS = 256;
 constexpr int WT_TPB = 256;  // 8 warps, 4 rows each
 
 __device__ __forceinline__ double key_to_value(uint64_t k) {
@@ -98,7 +97,8 @@ __device__ __forceinline__ double key_to_value(uint64_t k) {
     return __longlong_as_double((long long)b);
 }
 
-__global__ void __launch_bounds__(WT_TPB)
+template <int WT_COLS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WT_TPB, MIN_BLOCKS)
     topl_warp_kernel(const double* __restrict__ R, int64_t rows, int64_t cols, int64_t ld, int L,
                      int32_t* __restrict__ idx_out, double* __restrict__ val_out, int64_t ldv) {
     extern __shared__ double wt_tile[];  // [WT_ROWS][WT_COLS + 1]
@@ -988,10 +988,12 @@ int32_t launch_topl(ss_ctx* ctx, const double* R, int64_t rows, int64_t cols, in
                     double* val_out, int64_t ldv) {
     if (rows == 0) return SS_OK;
     if (L <= 32) {
+        // 32 x 256 tiles, two blocks per SM (measured: 128- and 64-column tiles with 3 / 4 blocks are 12 % / 25 % slower)
+        constexpr int WT_COLS = 256;
         const size_t wsm = size_t(WT_ROWS) * (WT_COLS + 1) * 8;
-        SS_CHECK_CUDA(cudaFuncSetAttribute(topl_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsm)));
-        topl_warp_kernel<<<unsigned(ceil_div(rows, WT_ROWS)), WT_TPB, wsm, ctx->stream>>>(R, rows, cols, ld, L, idx_out,
-                                                                                         val_out, ldv);
+        SS_CHECK_CUDA(cudaFuncSetAttribute(topl_warp_kernel<WT_COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsm)));
+        topl_warp_kernel<WT_COLS, 2><<<unsigned(ceil_div(rows, WT_ROWS)), WT_TPB, wsm, ctx->stream>>>(R, rows, cols, ld, L, idx_out,
+                                                                                                   val_out, ldv);
         SS_CHECK_CUDA(cudaGetLastError());
         ctx->launches++;
         return SS_OK;

@@ -80,7 +80,7 @@ def csr(alpha, weighted):
 
 
 nnz = csr(0.96, 1)
-report("featurize_csr (count + mask with lanes along rows, device scan, segment replay fill; weighted, alpha=0.96)", n, "elements",
+report("featurize_csr (count + keep-mask with lanes along rows, device-wide scan, mask-replay fill; weighted, alpha=0.96)", n, "elements",
        8 * n + 12 * nnz + 4 * rows,
        lambda: csr(0.96, 1), f"S read ONCE: 8 B per element + 12 B per kept edge ({nnz} edges, {nnz / n:.1%} dense); the fill pass "
        "replays the keep-mask of the count pass and touches only the sectors of kept entries; includes the host sync for nnz "
