@@ -15,6 +15,8 @@
 //   * tiles are rasterised in groups of 16 row-tiles so that the 148 concurrently processed
 //     tiles share A/B slabs through L2.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "ss_common.cuh"
 
@@ -161,6 +163,207 @@ __device__ __forceinline__ double finish(double acc, int row, int col, const Gem
     if (p.accumulate) v += *cptr;
     if (p.col_flag && __ldg(p.col_flag + col) == 0) v = -99.0;
     return v;
+}
+
+// ---- whole-tile kernel ---------------------------------------------------------------------------------------------
+// Launches that need no row bands (every large shape: C4 is 2 066 whole waves) run this kernel, which is the band
+// kernel below reduced to whole 128 x 128 tiles with the per-thread offsets hoisted out of the tile loop.  Kept as its
+// own kernel because ptxas schedules its K loop slightly better: 36.4 against 35.9 TFLOP/s on the C4 R product.
+constexpr int MT_WHOLE = WM / 8;
+
+// A_MMAJOR: A is M x K column-major (m contiguous) staged as 8 boxes [16 k][16 m] per slab.
+// !A_MMAJOR: A is stored K x M column-major (k contiguous) staged as one box [128 m][16 k].
+template <bool A_MMAJOR>
+__global__ void __launch_bounds__(THREADS, 1)
+    ss_dgemm_whole_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES]
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int kblocks = (p.K + BK - 1) / BK;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_base + 8 * s, 1);                          // full: producer's expect_tx
+            mbar_init(bar_base + 8 * (STAGES + s), CONSUMER_WARPS);  // empty: one arrive per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int checkpoint = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, p.tiles_m, p.tiles_n);
+                const int m0 = tc.tm * BM, n0 = tc.tn * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (p.sync_prog && (kb % SYNC_CHUNK) == 0) {
+                        // Loose lockstep.  The 148 CTAs of a wave share ~25 A/B panels through L2
+                        // only while they stream K at nearby positions; left alone they drift
+                        // apart, every slab is re-fetched from HBM (measured at C4: 10.6 TB
+                        // instead of ~1 TB) and the high fill rate shortens L2 residency further.
+                        // Each producer publishes a checkpoint count every SYNC_CHUNK slabs and
+                        // may run at most one checkpoint ahead of the slowest CTA, so jitter
+                        // averages out instead of adding up as with a hard per-tile barrier.
+                        // The wait is bounded: a CTA that is not co-resident cannot dead-lock us.
+                        ++checkpoint;
+                        *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = checkpoint;
+                        const long long t0 = clock64();
+                        for (;;) {
+                            int mn = 0x7fffffff;
+                            for (int i = 0; i < int(gridDim.x); ++i)
+                                mn = min(mn, *reinterpret_cast<volatile int*>(p.sync_prog + i));
+                            if (mn >= checkpoint - 1 || clock64() - t0 > 400000ll) break;
+                            __nanosleep(256);
+                        }
+                    }
+                    const uint32_t full = bar_base + 8 * stage;
+                    const uint32_t empty = bar_base + 8 * (STAGES + stage);
+                    mbar_wait(empty, phase ^ 1);
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const uint32_t sA = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sB = sA + A_BYTES;
+                    if (A_MMAJOR) {
+#pragma unroll
+                        for (int b = 0; b < BM / 16; ++b)
+                            tma_load_2d(sA + b * 2048, &mapA, m0 + b * 16, kb * BK, full);
+                    } else {
+                        tma_load_2d(sA, &mapA, kb * BK, m0, full);
+                    }
+                    tma_load_2d(sB, &mapB, kb * BK, n0, full);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            if (p.sync_prog) *reinterpret_cast<volatile int*>(p.sync_prog + blockIdx.x) = 0x7fffffff;
+        }
+        return;
+    }
+
+    // ================= DMMA consumers =================
+    const int g = lane >> 2, t = lane & 3;
+    const int rg = rho(g);
+    const int m_warp = (warp / WARPS_N) * WM;
+    const int n_warp = (warp % WARPS_N) * WN;
+
+    // per-thread shared-memory offsets (bytes, relative to the stage's A / B base)
+    // B (k-major): row n = n_warp + 8j + rho(g); chunk (t + 4h) ^ rho(g)
+    uint32_t offB[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) offB[h] = (n_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
+    // A k-major: row m = m_warp + 8i + rho(g), same chunk rule
+    uint32_t offAk[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) offAk[h] = (m_warp + rg) * 128 + (((t + 4 * h) ^ rg) << 4);
+    // A m-major: block (m_warp/16 + b), row k = 2t + (s&1) + 8(s>>1), chunk g ^ (k & 7)
+    uint32_t offAm[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int k = 2 * t + (s & 1) + 8 * (s >> 1);
+        offAm[s] = (m_warp >> 4) * 2048 + k * 128 + ((g ^ (k & 7)) << 4);
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(tile, p.tiles_m, p.tiles_n);
+        const int m0 = tc.tm * BM, n0 = tc.tn * BN;
+
+        double acc[MT_WHOLE][NT][2];
+#pragma unroll
+        for (int i = 0; i < MT_WHOLE; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(bar_base + 8 * stage, phase);
+            const uint32_t sA = smem_base + stage * STAGE_BYTES;
+            const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double2 bf[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bf[j] = lds128(sB + offB[h] + j * 8 * 128);
+                if (A_MMAJOR) {
+#pragma unroll
+                    for (int ss2 = 0; ss2 < 2; ++ss2) {
+                        const int s = 2 * h + ss2;
+                        double2 af[MT_WHOLE / 2];
+#pragma unroll
+                        for (int b = 0; b < MT_WHOLE / 2; ++b) af[b] = lds128(sA + offAm[s] + b * 2048);
+#pragma unroll
+                        for (int b = 0; b < MT_WHOLE / 2; ++b)
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const double bv = ss2 ? bf[j].y : bf[j].x;
+                                dmma(acc[2 * b][j], af[b].x, bv);
+                                dmma(acc[2 * b + 1][j], af[b].y, bv);
+                            }
+                    }
+                } else {
+                    double2 af[MT_WHOLE];
+#pragma unroll
+                    for (int i = 0; i < MT_WHOLE; ++i) af[i] = lds128(sA + offAk[h] + i * 8 * 128);
+#pragma unroll
+                    for (int ss2 = 0; ss2 < 2; ++ss2)
+#pragma unroll
+                        for (int i = 0; i < MT_WHOLE; ++i)
+#pragma unroll
+                            for (int j = 0; j < NT; ++j)
+                                dmma(acc[i][j], ss2 ? af[i].y : af[i].x, ss2 ? bf[j].y : bf[j].x);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+
+        // ---- epilogue: registers -> global (column-major C), fused normalisation / clean! ----
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = n0 + n_warp + 8 * j + t + 4 * e;  // rho(2t+e) = t + 4e
+                if (col >= p.N) continue;
+                const int64_t coff = int64_t(col) * p.ldc;
+                const double* ccol = p.C + coff;
+                if (A_MMAJOR) {
+#pragma unroll
+                    for (int b = 0; b < MT_WHOLE / 2; ++b) {
+                        const int row = m0 + m_warp + 16 * b + 2 * g;  // rows (row, row+1)
+                        if (row + 1 < p.M && p.cvec) {
+                            double2 v;
+                            v.x = finish(acc[2 * b][j][e], row, col, p, ccol + row);
+                            v.y = finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1);
+                            store2(p, coff + row, v);
+                        } else {
+                            if (row < p.M) store1(p, coff + row, finish(acc[2 * b][j][e], row, col, p, ccol + row));
+                            if (row + 1 < p.M)
+                                store1(p, coff + row + 1,
+                                       finish(acc[2 * b + 1][j][e], row + 1, col, p, ccol + row + 1));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < MT_WHOLE; ++i) {
+                        const int row = m0 + m_warp + 8 * i + rg;
+                        if (row < p.M) store1(p, coff + row, finish(acc[i][j][e], row, col, p, ccol + row));
+                    }
+                }
+            }
+    }
 }
 
 // One work unit of the consumer warps: the (MT_ * 16) x 128 row band `band` of tile (m0, n0), warp tile (MT_ * 8) x 32.
@@ -524,6 +727,10 @@ static int32_t launch_gemm_f64_one(ss_ctx* ctx, int opA, const double* A, int64_
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
         SS_CHECK_CUDA(cudaFuncSetAttribute(ss_dgemm_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+        SS_CHECK_CUDA(cudaFuncSetAttribute(ss_dgemm_whole_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+        SS_CHECK_CUDA(cudaFuncSetAttribute(ss_dgemm_whole_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
         ctx->gemm_attr_set = true;
     }
     ss_ctx::ProfRec rec{nullptr, nullptr, 2.0 * double(M) * double(N) * double(K)};
@@ -532,10 +739,17 @@ static int32_t launch_gemm_f64_one(ss_ctx* ctx, int opA, const double* A, int64_
         SS_CHECK_CUDA(cudaEventCreate(&rec.stop));
         SS_CHECK_CUDA(cudaEventRecord(rec.start, ctx->stream));
     }
-    if (opA == SS_OP_N)
+    const char* force = getenv("SS_GEMM_KERNEL");  // "bands": the band kernel for whole tiles too (A/B measurements)
+    if (split == 1 && !(force && !strcmp(force, "bands"))) {
+        if (opA == SS_OP_N)
+            ss_dgemm_whole_kernel<true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
+        else
+            ss_dgemm_whole_kernel<false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
+    } else if (opA == SS_OP_N) {
         ss_dgemm_kernel<true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
-    else
+    } else {
         ss_dgemm_kernel<false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
+    }
     SS_CHECK_CUDA(cudaGetLastError());
     if (ctx->profile) {
         SS_CHECK_CUDA(cudaEventRecord(rec.stop, ctx->stream));

@@ -512,8 +512,11 @@ def test_gemm_partial_wave_in_row_bands_is_bit_identical(ss, M, N, K, op):
     df = ss.DIVec.from_host(ctx, rng.integers(0, 2, size=N).astype(np.int32))
     o_ = SS_OP_N if op == "N" else SS_OP_T
     res = {}
-    for split in ("0", "2", "4"):
-        os.environ["SS_GEMM_TAIL_SPLIT"] = split
+    # "0": whole tiles on the whole-tile kernel (what large shapes run); "0b": whole tiles on the band kernel
+    for split in ("0", "0b", "2", "4"):
+        os.environ["SS_GEMM_TAIL_SPLIT"] = split[0]
+        if split == "0b":
+            os.environ["SS_GEMM_KERNEL"] = "bands"
         try:
             dC, dE = ss.DMat(ctx, M, N), ss.DMat(ctx, M, N)
             check(ss.lib().ss_gemm_f64(ctx.h, o_, dA.h, dB.h, dC.h, None, None))
@@ -521,10 +524,11 @@ def test_gemm_partial_wave_in_row_bands_is_bit_identical(ss, M, N, K, op):
             res[split] = (dC.to_host(), dE.to_host())
         finally:
             os.environ.pop("SS_GEMM_TAIL_SPLIT", None)
+            os.environ.pop("SS_GEMM_KERNEL", None)
     want = A @ B
     bound = np.abs(A) @ np.abs(B)
     assert np.max(np.abs(res["0"][0] - want) / bound) < 1e-13
-    for split in ("2", "4"):
+    for split in ("0b", "2", "4"):
         assert np.array_equal(res[split][0], res["0"][0]) and np.array_equal(res[split][1], res["0"][1])
 
 
