@@ -112,6 +112,8 @@ SS_API int32_t ss_mat_wrap(ss_ctx* ctx, void* devptr, int64_t rows, int64_t cols
 SS_API int32_t ss_mat_destroy(ss_mat* m);
 SS_API int32_t ss_mat_info(const ss_mat* m, int64_t* rows, int64_t* cols, int64_t* ld, void** devptr);
 SS_API int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host);
+/* row-major host array (row pitch ld_host >= cols, NumPy's default order): uploaded as it lies, transposed on the device */
+SS_API int32_t ss_mat_upload_rowmajor(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host);
 SS_API int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_host);
 /* column range [col0, col0+ncols) only; asynchronous on the context stream (pinned host memory) */
 SS_API int32_t ss_mat_upload_cols_async(ss_ctx* ctx, ss_mat* m, int64_t col0, int64_t ncols,

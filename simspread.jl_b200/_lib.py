@@ -47,6 +47,7 @@ SIGNATURES = {
     "ss_mat_destroy": (c_i32, [vp]),
     "ss_mat_info": (c_i32, [vp, P(c_i64), P(c_i64), P(c_i64), P(vp)]),
     "ss_mat_upload": (c_i32, [vp, vp, vp, c_i64]),
+    "ss_mat_upload_rowmajor": (c_i32, [vp, vp, vp, c_i64]),
     "ss_mat_download": (c_i32, [vp, vp, vp, c_i64]),
     "ss_mat_upload_cols_async": (c_i32, [vp, vp, c_i64, c_i64, vp, c_i64]),
     "ss_mat_download_cols_async": (c_i32, [vp, vp, c_i64, c_i64, vp, c_i64]),

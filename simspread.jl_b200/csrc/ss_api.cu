@@ -450,6 +450,35 @@ int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_hos
     return SS_OK;
 }
 
+// Row-major host array (rows x cols, row pitch ld_host >= cols; NumPy's default order) into a column-major device
+// matrix: the array is the column-major image of its transpose, so it is uploaded as it lies (staged copy for pageable
+// memory) and transposed on the device -- instead of a strided transposing copy on the host (0.3 s for 800 MB in NumPy).
+int32_t ss_mat_upload_rowmajor(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host) {
+    SS_ENTER(ctx);
+    SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_upload_rowmajor: null argument");
+    SS_REQUIRE(ld_host >= m->cols, "ss_mat_upload_rowmajor: ld_host (%lld) < cols (%lld)", (long long)ld_host,
+               (long long)m->cols);
+    if (m->rows == 0 || m->cols == 0) return SS_OK;
+    const int64_t ldt = round_up(m->cols, 16);
+    double* tmp = nullptr;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&tmp), size_t(ldt) * size_t(m->rows) * 8, ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("ss_mat_upload_rowmajor: out of device memory for the %lld x %lld staging copy", (long long)m->cols,
+                  (long long)m->rows);
+        return SS_ERR_OOM;
+    }
+    int32_t st;
+    if (m->rows * m->cols * 8 >= kStagedCopyMinBytes && host_is_pageable(host)) {
+        st = staged_copy2d(ctx, tmp, ldt, const_cast<double*>(host), ld_host, m->cols, m->rows, true);
+    } else {
+        st = copy2d(ctx, ctx->stream, tmp, ldt, host, ld_host, m->cols, m->rows, cudaMemcpyHostToDevice);
+    }
+    if (st == SS_OK) st = launch_transpose(ctx, tmp, ldt, m->d, m->ld, m->rows, m->cols);
+    cudaFreeAsync(tmp, ctx->stream);
+    SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return st;
+}
+
 int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_host) {
     SS_ENTER(ctx);
     SS_REQUIRE(m && (host || m->rows * m->cols == 0), "ss_mat_download: null argument");

@@ -106,6 +106,8 @@ int32_t launch_featurize(ss_ctx* ctx, const double* S, int64_t rows, int64_t col
                          double alpha, bool weighted, double* X, int64_t ldx);
 int32_t launch_gather(ss_ctx* ctx, const double* src, int64_t lds, const int32_t* ridx,
                       const int32_t* cidx, double* dst, int64_t rows, int64_t cols, int64_t ldd);
+int32_t launch_transpose(ss_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows,
+                         int64_t cols);
 int32_t launch_degrees(ss_ctx* ctx, const double* M, int64_t rows, int64_t cols, int64_t ld,
                        int32_t* row_deg, int32_t* col_deg);  // accumulates into row_deg (+=)
 int32_t launch_spread_rows(ss_ctx* ctx, const double* G, int64_t rows, int64_t cols, int64_t ldg,

@@ -192,6 +192,32 @@ inline unsigned pick_grid_y(const ss_ctx* ctx, int64_t gx, int64_t cols, int wav
 
 }  // namespace
 
+namespace {
+
+// dst (rows x cols, column-major, ld ldd) = transpose of src (cols x rows, column-major, ld lds): the device half of
+// ss_mat_upload_rowmajor (a row-major host array is the column-major image of its transpose).  32 x 32 tiles through
+// padded shared memory, both sides coalesced.
+__global__ void __launch_bounds__(256)
+    transpose_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd, int64_t rows,
+                     int64_t cols) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of the tile per pass
+    const int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
+    // src element (c, r) at src[r * lds + c]: lanes along c
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t r = r0 + j, c = c0 + tx;
+        tile[j][tx] = (r < rows && c < cols) ? src[r * lds + c] : 0.0;
+    }
+    __syncthreads();
+    // dst element (r, c) at dst[c * ldd + r]: lanes along r
+    for (int j = ty; j < 32; j += 8) {
+        const int64_t c = c0 + j, r = r0 + tx;
+        if (r < rows && c < cols) dst[c * ldd + r] = tile[tx][j];
+    }
+}
+
+}  // namespace
+
 namespace ss {
 
 int32_t launch_featurize(ss_ctx* ctx, const double* S, int64_t rows, int64_t cols, int64_t lds,
@@ -203,6 +229,17 @@ int32_t launch_featurize(ss_ctx* ctx, const double* S, int64_t rows, int64_t col
     const int64_t gx = ceil_div(ceil_div(rows, 2), TPB);
     dim3 grid(unsigned(gx), pick_grid_y(ctx, gx, cols, 16));
     featurize_kernel<<<grid, TPB, 0, ctx->stream>>>(S, rows, cols, lds, alpha, weighted ? 1 : 0, X, ldx);
+    SS_CHECK_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SS_OK;
+}
+
+int32_t launch_transpose(ss_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows,
+                         int64_t cols) {
+    if (rows == 0 || cols == 0) return SS_OK;
+    SS_REQUIRE(ceil_div(rows, 32) <= 65535, "transpose: more than 2 M rows are not supported");
+    const dim3 grid(unsigned(ceil_div(cols, 32)), unsigned(ceil_div(rows, 32)));
+    transpose_kernel<<<grid, 256, 0, ctx->stream>>>(src, lds, dst, ldd, rows, cols);
     SS_CHECK_CUDA(cudaGetLastError());
     ctx->launches++;
     return SS_OK;

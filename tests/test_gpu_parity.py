@@ -204,6 +204,23 @@ def test_degrees_exact(ss, o, ns, nf, nt):
     assert np.array_equal(ss.spread(G), o.spread(G))
 
 
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 70), (445, 664), (1000, 33), (2100, 2300)])
+def test_row_major_upload_is_transposed_on_the_device(ss, rows, cols):
+    """NumPy's default order goes up as it lies and is transposed by `transpose_kernel` (ss_mat_upload_rowmajor);
+    the device image must equal the column-major upload of the same matrix (2100 x 2300 = 38 MB takes the staged
+    pageable-memory copy)."""
+    rng = np.random.default_rng(rows + cols)
+    a = rng.standard_normal((rows, cols))
+    assert a.flags.c_contiguous
+    ctx = ss.Context.default()
+    got = ss.DMat.from_host(ctx, a).to_host()
+    want = ss.DMat.from_host(ctx, np.asfortranarray(a)).to_host()
+    assert np.array_equal(got, a) and np.array_equal(want, a)
+    # a row-major view with a pitch (every second column block of a wider array) takes the generic path
+    wide = rng.standard_normal((rows, 2 * cols))
+    assert np.array_equal(ss.DMat.from_host(ctx, wide[:, :cols]).to_host(), wide[:, :cols])
+
+
 GEMM_SHAPES = [(1, 1, 1), (5, 3, 2), (128, 128, 16), (129, 127, 17), (300, 200, 100), (45, 664, 400),
                (1000, 37, 555), (64, 1500, 1031)]
 
