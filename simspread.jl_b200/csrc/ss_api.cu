@@ -375,6 +375,50 @@ static void parallel_copy_cols(char* dst, size_t dpitch, const char* src, size_t
 // download of finished column blocks overlaps the kernels that produce the next ones.  `cchunk_cols` overrides the
 // number of columns per staging chunk (it must divide ready_cols).
 static constexpr size_t kStage = size_t(128) << 20;
+static int32_t ensure_stage(ss_ctx* ctx) {
+    if (!ctx->stage[0]) {
+        for (int i = 0; i < 3; ++i) {
+            SS_CHECK_CUDA(cudaHostAlloc(&ctx->stage[i], kStage, cudaHostAllocDefault));
+            SS_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    return SS_OK;
+}
+
+// Medium-sized pageable copies (256 KB .. 32 MB: the matrices of a C2-sized cross-validation): one pinned staging
+// buffer, packed / unpacked by the calling thread.  cudaMemcpy on pageable memory took 0.77 ms for a 2.4 MB download;
+// DMA into pinned memory + one memcpy is ~3 x faster.
+static int32_t small_staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host, int64_t ldh, int64_t rows, int64_t cols,
+                                   bool upload) {
+    SS_TRY(ensure_stage(ctx));
+    std::lock_guard<std::mutex> pool_guard(g_copy_pool_mutex);
+    const size_t row_bytes = size_t(rows) * 8;
+    char* st = static_cast<char*>(ctx->stage[0]);
+    SS_CHECK_CUDA(cudaEventSynchronize(ctx->stage_ev[0]));  // a DMA that last used this buffer is done
+    if (upload) {
+        if (ldh == rows) {
+            memcpy(st, host, row_bytes * size_t(cols));
+        } else {
+            for (int64_t c = 0; c < cols; ++c) memcpy(st + size_t(c) * row_bytes, host + c * ldh, row_bytes);
+        }
+        SS_CHECK_CUDA(cudaMemcpy2DAsync(dev, size_t(ldd) * 8, st, row_bytes, row_bytes, size_t(cols), cudaMemcpyHostToDevice,
+                                        ctx->stream));
+        SS_CHECK_CUDA(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        SS_CHECK_CUDA(cudaMemcpy2DAsync(st, row_bytes, dev, size_t(ldd) * 8, row_bytes, size_t(cols), cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+        SS_CHECK_CUDA(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+        SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ldh == rows) {
+            memcpy(host, st, row_bytes * size_t(cols));
+        } else {
+            for (int64_t c = 0; c < cols; ++c) memcpy(host + c * ldh, st + size_t(c) * row_bytes, row_bytes);
+        }
+    }
+    return SS_OK;
+}
+
 static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host, int64_t ldh, int64_t rows, int64_t cols,
                              bool upload, const cudaEvent_t* ready = nullptr, int64_t ready_cols = 0,
                              int64_t cchunk_cols = 0) {
@@ -386,12 +430,7 @@ static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host
         SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
         return SS_OK;
     }
-    if (!ctx->stage[0]) {
-        for (int i = 0; i < kBufs; ++i) {
-            SS_CHECK_CUDA(cudaHostAlloc(&ctx->stage[i], kStage, cudaHostAllocDefault));
-            SS_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
-        }
-    }
+    SS_TRY(ensure_stage(ctx));
     std::lock_guard<std::mutex> pool_guard(g_copy_pool_mutex);
     const int nthreads = copy_pool().size();
     const int64_t cchunk = cchunk_cols > 0 ? cchunk_cols : std::max<int64_t>(1, int64_t(kStage / row_bytes));
@@ -437,6 +476,7 @@ static int32_t staged_copy2d(ss_ctx* ctx, double* dev, int64_t ldd, double* host
 }
 
 static constexpr int64_t kStagedCopyMinBytes = int64_t(32) << 20;
+static constexpr int64_t kSmallStageMinBytes = int64_t(256) << 10;
 
 int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_host) {
     SS_ENTER(ctx);
@@ -445,6 +485,8 @@ int32_t ss_mat_upload(ss_ctx* ctx, ss_mat* m, const double* host, int64_t ld_hos
                (long long)m->rows);
     if (m->rows * m->cols * 8 >= kStagedCopyMinBytes && host_is_pageable(host))
         return staged_copy2d(ctx, m->d, m->ld, const_cast<double*>(host), ld_host, m->rows, m->cols, true);
+    if (m->rows * m->cols * 8 >= kSmallStageMinBytes && host_is_pageable(host))
+        return small_staged_copy2d(ctx, m->d, m->ld, const_cast<double*>(host), ld_host, m->rows, m->cols, true);
     SS_TRY(copy2d(ctx, ctx->stream, m->d, m->ld, host, ld_host, m->rows, m->cols, cudaMemcpyHostToDevice));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;
@@ -486,6 +528,8 @@ int32_t ss_mat_download(ss_ctx* ctx, const ss_mat* m, double* host, int64_t ld_h
                (long long)m->rows);
     if (m->rows * m->cols * 8 >= kStagedCopyMinBytes && host_is_pageable(host))
         return staged_copy2d(ctx, m->d, m->ld, host, ld_host, m->rows, m->cols, false);
+    if (m->rows * m->cols * 8 >= kSmallStageMinBytes && host_is_pageable(host))
+        return small_staged_copy2d(ctx, m->d, m->ld, host, ld_host, m->rows, m->cols, false);
     SS_TRY(copy2d(ctx, ctx->stream, host, ld_host, m->d, m->ld, m->rows, m->cols, cudaMemcpyDeviceToHost));
     SS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return SS_OK;

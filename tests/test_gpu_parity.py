@@ -213,7 +213,12 @@ def test_row_major_upload_is_transposed_on_the_device(ss, rows, cols):
     a = rng.standard_normal((rows, cols))
     assert a.flags.c_contiguous
     ctx = ss.Context.default()
-    got = ss.DMat.from_host(ctx, a).to_host()
+    from simspread_b200 import host as _host
+    old_min, _host._ROWMAJOR_UPLOAD_MIN_BYTES = _host._ROWMAJOR_UPLOAD_MIN_BYTES, 0  # small arrays too
+    try:
+        got = ss.DMat.from_host(ctx, a).to_host()
+    finally:
+        _host._ROWMAJOR_UPLOAD_MIN_BYTES = old_min
     want = ss.DMat.from_host(ctx, np.asfortranarray(a)).to_host()
     assert np.array_equal(got, a) and np.array_equal(want, a)
     # a row-major view with a pitch (every second column block of a wider array) takes the generic path
