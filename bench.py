@@ -494,7 +494,7 @@ def run_b200(args):
             except Exception:
                 traffic = None
         roofline = {
-            "bound": "tensor", "kernel": "ss_dgemm_kernel<A_MMAJOR> (R = Xq*T, FP64 DMMA)",
+            "bound": "tensor", "kernel": "ss_dgemm_whole_kernel<A_MMAJOR> (R = Xq*T, FP64 DMMA; whole 128 x 128 tiles)",
             "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
             "traffic": traffic,
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run, best of 5; "

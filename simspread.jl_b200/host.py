@@ -1014,17 +1014,26 @@ def alpha_sweep(DT: NamedArray, DD: NamedArray, queries: Sequence[str], alphas: 
     out = []
     ctx.sync()
     t_setup = _time.perf_counter()
+    kx = DIVec(ctx, len(qi))
     for a in list(alphas)[rank::world]:
-        use_sparse = False
+        use_sparse, have_xq = False, False
         if layout != "dense" and len(qi) and len(si) and len(fi):
-            cq = DCsr.from_dense(ctx, Sq, float(a), bool(weighted))
-            if layout == "sparse" or cq.density < SPARSE_DENSITY_THRESHOLD:
+            maybe = layout == "sparse"
+            if not maybe:  # density of the query block from its thresholded form (needed by the dense chain anyway):
+                check(lib().ss_featurize(ctx.h, Sq.h, float(a), w, Xq.h))  # no CSR is built just to be thrown away
+                check(lib().ss_k_rows(ctx.h, Xq.h, kx.h))
+                have_xq = True
+                maybe = kx.to_host().astype(np.int64).sum() < SPARSE_DENSITY_THRESHOLD * len(qi) * len(fi)
+            if maybe:
+                cq = DCsr.from_dense(ctx, Sq, float(a), bool(weighted))
                 cs = DCsr.from_dense(ctx, Ss, float(a), bool(weighted), by_columns=True)
-                use_sparse = layout == "sparse" or cs.density < SPARSE_DENSITY_THRESHOLD
+                use_sparse = layout == "sparse" or (cq.density < SPARSE_DENSITY_THRESHOLD
+                                                    and cs.density < SPARSE_DENSITY_THRESHOLD)
         if use_sparse:
             check(lib().ss_predict_query_csr(ctx.h, cq.h, cs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
         else:
-            check(lib().ss_featurize(ctx.h, Sq.h, float(a), w, Xq.h))
+            if not have_xq:
+                check(lib().ss_featurize(ctx.h, Sq.h, float(a), w, Xq.h))
             check(lib().ss_featurize(ctx.h, Ss.h, float(a), w, Xs.h))
             check(lib().ss_predict_query(ctx.h, Xq.h, Xs.h, Y.h, R.h, SS_PREDICT_CLEAN, None))
         auc, atl = (C.c_double * 2)(), (C.c_double * 2)()
