@@ -1,0 +1,41 @@
+"""One launch each of the kernels changed late in round 2, for `ncu --set full` (tools/gpu_run.sh prof): the band form of
+the DMMA GEMM on the C3 shape, the CSR build (count + fill) and the warp-level top-L at C4-like sizes."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simspread_b200 as ss
+from simspread_b200._lib import SS_OP_N, check
+
+ctx = ss.Context(0)
+L = ss.lib()
+dev = torch.device("cuda:0")
+
+
+def colmajor(rows, cols):
+    ld = (rows + 15) // 16 * 16
+    buf = torch.empty((cols, ld), dtype=torch.float64, device=dev)
+    for c0 in range(0, cols, 2000):
+        blk = buf[c0:c0 + 2000]
+        blk.copy_(torch.round(torch.rand(blk.shape, device=dev, dtype=torch.float64) * 1e6) / 1e6)
+    torch.cuda.synchronize()
+    return buf, ss.DMat.wrap(ctx, buf.data_ptr(), rows, cols, ld)
+
+
+bA, mA = colmajor(5000, 5000)
+bB, mB = colmajor(5000, 2000)
+bC, mC = colmajor(5000, 2000)
+for _ in range(2):
+    check(L.ss_gemm_f64(ctx.h, SS_OP_N, mA.h, mB.h, mC.h, None, None))
+bS, mS = colmajor(50_000, 20_000)
+for _ in range(2):
+    h = C.c_void_p()
+    check(L.ss_featurize_csr(ctx.h, mS.h, 0.96, 1, C.byref(h)))
+    L.ss_csr_destroy(h)
+idx = ss.DIVec(ctx, 20 * 50_000)
+for _ in range(2):
+    check(L.ss_topl_rows(ctx.h, mS.h, 20, idx.h, None))
+ctx.sync()
