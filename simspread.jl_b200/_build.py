@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsimspread_b200.so"
-SOURCES = ["ss_api.cu", "ss_elementwise.cu", "ss_gemm.cu", "ss_csr.cu", "ss_rank.cu", "ss_sparse.cu", "ss_umma.cu", "ss_recsys.cu", "ss_transfer.cu", "ss_comm.cu", "ss_folds.cu", "ss_similarity.cu", "ss_io.cu"]
+SOURCES = ["ss_api.cu", "ss_elementwise.cu", "ss_gemm.cu", "ss_csr.cu", "ss_rank.cu", "ss_sparse.cu", "ss_umma.cu", "ss_recsys.cu", "ss_transfer.cu", "ss_comm.cu", "ss_folds.cu", "ss_similarity.cu", "ss_io.cu", "ss_tsparse.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

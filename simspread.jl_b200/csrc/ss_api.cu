@@ -941,8 +941,10 @@ struct ChainWs {
     int64_t ldt = 0;
 };
 
+// need_wst: the caller also reads Wst (predict_source); otherwise a sparse label matrix takes the edge-list form of the
+// first product (csrc/ss_tsparse.cu) and Wst is never materialised.
 static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ChainWs* w,
-                           uint32_t precision = SS_PRECISION_F64) {
+                           uint32_t precision = SS_PRECISION_F64, bool need_wst = false) {
     const int64_t ns = Y->rows, nt = Y->cols, nf = Xs ? Xs->cols : 0;
     void* p;
     const size_t kbytes = size_t(round_up(ns, 64) + round_up(nf, 64) + round_up(nt, 64)) * 4;
@@ -964,6 +966,15 @@ static int32_t chain_front(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, Chain
         w->T = static_cast<double*>(p);
         SS_TRY(chain_gemm(ctx, precision, SS_OP_T, Xk, ldx, Y->d, Y->ld, w->T, w->ldt, nf, nt, ns, w->kf, nullptr));
         return SS_OK;
+    }
+    if (Xs && !need_wst && precision == SS_PRECISION_F64) {
+        w->ldt = round_up(nf, 16);
+        SS_TRY(scratch_get(ctx, 2, size_t(w->ldt) * size_t(nt) * 8, &p));
+        w->T = static_cast<double*>(p);
+        bool used = false;
+        SS_TRY(t_from_sparse_labels(ctx, Xs->d, Xs->ld, Y->d, Y->ld, ns, nf, nt, w->ks, w->kf, w->kt, w->T, w->ldt, 0, nullptr,
+                                    &used));
+        if (used) return SS_OK;
     }
     w->ldw = round_up(ns, 16);
     SS_TRY(scratch_get(ctx, 1, size_t(w->ldw) * size_t(nt) * 8, &p));
@@ -1180,7 +1191,7 @@ int32_t ss_predict_source(ss_ctx* ctx, const ss_mat* Xs, const ss_mat* Y, ss_mat
     if (R->rows == 0 || R->cols == 0) return SS_OK;
     const ss_mat* Xeff = (Xs && Xs->cols > 0) ? Xs : nullptr;
     ChainWs w;
-    SS_TRY(chain_front(ctx, Xeff, Y, &w));
+    SS_TRY(chain_front(ctx, Xeff, Y, &w, SS_PRECISION_F64, true));
     const int64_t ns = Y->rows, nt = Y->cols;
     // U[t',t] = (sum_s Y[s,t'] * Wst[s,t]) / kt[t']
     void* p;

@@ -441,10 +441,16 @@ int32_t ss_sharded_front(ss_sharded* p, const ss_mat* Xs, const ss_mat* Yblk) {
     } else {
         SS_CHECK_CUDA(cudaMemcpyAsync(p->kt, p->kt_blk, size_t(p->nt_blk) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    SS_TRY(launch_spread_rows(ctx, Yblk->d, p->ns, p->nt_blk, Yblk->ld, p->ks, p->Wst, p->ldw));
     double* Tblk = p->T + size_t(c->rank) * p->nt_blk * p->ldt;
-    SS_TRY(launch_gemm_f64(ctx, SS_OP_T, Xs->d, Xs->ld, p->Wst, p->ldw, Tblk, p->ldt, p->nf, p->nt_blk, p->ns, p->kf, nullptr, false,
-                           p->fused ? p->n_mirrors : 0, p->fused ? p->mirrors : nullptr));
+    // sparse labels: T block from the edge list of the Y block (csrc/ss_tsparse.cu), stored into every peer's T as well
+    bool used = false;
+    SS_TRY(t_from_sparse_labels(ctx, Xs->d, Xs->ld, Yblk->d, Yblk->ld, p->ns, p->nf, p->nt_blk, p->ks, p->kf, p->kt_blk, Tblk, p->ldt,
+                                p->fused ? p->n_mirrors : 0, p->fused ? p->mirrors : nullptr, &used));
+    if (!used) {
+        SS_TRY(launch_spread_rows(ctx, Yblk->d, p->ns, p->nt_blk, Yblk->ld, p->ks, p->Wst, p->ldw));
+        SS_TRY(launch_gemm_f64(ctx, SS_OP_T, Xs->d, Xs->ld, p->Wst, p->ldw, Tblk, p->ldt, p->nf, p->nt_blk, p->ns, p->kf, nullptr, false,
+                               p->fused ? p->n_mirrors : 0, p->fused ? p->mirrors : nullptr));
+    }
     if (c->world > 1) {
         if (p->fused) {
             SS_TRY(comm_barrier(c));  // every rank's epilogue has stored its block into every T

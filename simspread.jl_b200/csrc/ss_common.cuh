@@ -59,11 +59,12 @@ struct ss_ctx {
     int64_t int8_stats[3] = {0, 0, 0};
     int int8_last_pairs = 0;  // slice pairs of the last int8 product (planes of zeros are skipped)
     // workspaces reused across predict calls (never shrink)
-    ss::Scratch ws[24];
+    ss::Scratch ws[28];
     int32_t* tile_counter = nullptr;
     void* stage[3] = {nullptr, nullptr, nullptr};  // pinned staging buffers of the pageable-memory copies
     cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     bool gemm_attr_set = false;
+    bool tsp_attr_set = false;
     // optional per-GEMM timing (ss_ctx_profile)
     bool profile = false;
     struct ProfRec {
@@ -124,6 +125,11 @@ int32_t launch_gemm_tf32(ss_ctx* ctx, int opA, const double* A, int64_t lda, con
 int32_t launch_gemm_i8(ss_ctx* ctx, int opA, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                        int64_t ldc, int64_t M, int64_t N, int64_t K, const int32_t* row_div, const int32_t* col_flag,
                        int S, double cert_tol, int64_t* uncertified);
+// T = (Xs' * (Y ./ ks)) ./ kf from the edges of a sparse label matrix (csrc/ss_tsparse.cu); *used = false: declined,
+// the caller runs spread + the dense GEMM
+int32_t t_from_sparse_labels(ss_ctx* ctx, const double* Xs, int64_t ldxs, const double* Y, int64_t ldy, int64_t ns, int64_t nf,
+                             int64_t nt, const int32_t* ks, const int32_t* kf, const int32_t* kt, double* T, int64_t ldt,
+                             int nmirror, double* const* mirrors, bool* used);
 int32_t featurize_csr(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t featurize_csc(ss_ctx* ctx, const ss_mat* S, double alpha, bool weighted, ss_csr** out);
 int32_t predict_query_csr(ss_ctx* ctx, const ss_csr* Xq, const ss_csr* XsT, const ss_mat* Y, ss_mat* R, uint32_t flags,

@@ -488,6 +488,58 @@ def test_predict_query_fetch_overlapped_download(ss, o, nq, ns, nf, nt):
     assert np.array_equal(yh.array, want)
 
 
+@pytest.mark.parametrize("nq,ns,nf,nt", [(200, 300, 260, 170), (64, 1000, 129, 515), (33, 70, 64, 128), (10, 65, 1, 1)])
+def test_first_product_from_sparse_labels(ss, o, nq, ns, nf, nt):
+    """csrc/ss_tsparse.cu: T = (Xs' * (Y ./ ks)) ./ kf from the edge list of the label matrix (what the chain runs for a
+    large problem with sparse labels; forced here with SS_T_FORM=sparse) against the dense DMMA form and the oracle:
+    ragged tiles, a target without sources, a source without targets, a feature nobody has, NaN / Inf labels (edges
+    whose weight spread() sets to 0), and the decline on non-finite feature weights."""
+    from simspread_b200._lib import SS_PREDICT_CLEAN, check
+    Xq, Xs, Y = o.synth_dense(nq, ns, nf, nt, seed=nq + nt, y_density=0.06, alpha=0.3, weighted=True)
+    Y[:, 0] = 0.0
+    Y[min(5, ns - 1), :] = 0.0
+    Xs[:, nf // 2] = 0.0
+    if nt > 3:
+        Y[min(7, ns - 1), 2] = np.nan
+        Y[min(9, ns - 1), 3] = np.inf
+    ctx = ss.Context.default()
+    dq, dx, dy = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y))
+    res = {}
+    for form in ("dense", "sparse"):
+        os.environ["SS_T_FORM"] = form
+        try:
+            R = ss.DMat(ctx, nq, nt)
+            l0 = ctx.launch_count()
+            check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+            res[form] = (R.to_host(), ctx.launch_count() - l0)
+        finally:
+            os.environ.pop("SS_T_FORM", None)
+    assert res["sparse"][1] != res["dense"][1]  # the edge-list form really ran (scan, transpose, fill, product)
+    want = o.predict_blocks_query(Xq, Xs, Y)
+    o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
+    for form in ("dense", "sparse"):
+        got = res[form][0]
+        assert np.array_equal(got == -99, want == -99)
+        assert relerr(got, want) < RTOL
+    # two runs of the edge-list form are bit-identical (fixed summation order), and independent of the query rows
+    os.environ["SS_T_FORM"] = "sparse"
+    try:
+        R2 = ss.DMat(ctx, nq, nt)
+        check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R2.h, SS_PREDICT_CLEAN, None))
+        assert np.array_equal(R2.to_host(), res["sparse"][0], equal_nan=True)
+        # a non-finite feature weight: 0 * Inf = NaN in the dense product -> the edge-list form declines
+        Xs2 = Xs.copy()
+        Xs2[0, 0] = np.inf
+        dx2 = ss.DMat.from_host(ctx, Xs2)
+        R3, R4 = ss.DMat(ctx, nq, nt), ss.DMat(ctx, nq, nt)
+        check(ss.lib().ss_predict_query(ctx.h, dq.h, dx2.h, dy.h, R3.h, SS_PREDICT_CLEAN, None))
+        os.environ["SS_T_FORM"] = "dense"
+        check(ss.lib().ss_predict_query(ctx.h, dq.h, dx2.h, dy.h, R4.h, SS_PREDICT_CLEAN, None))
+        assert np.array_equal(R3.to_host(), R4.to_host(), equal_nan=True)
+    finally:
+        os.environ.pop("SS_T_FORM", None)
+
+
 def test_gemm_k_blocking_switch(ss, o):
     """SS_GEMM_KBLOCK (experiment switch, off by default) runs the second product as accumulating launches over blocks
     of the feature dimension; clean! is applied by the last block only."""
@@ -738,8 +790,9 @@ def _sharded_rank_main(rank, world, path, nq, ns, nf, nt, out_dir):
     comm.close()
 
 
+@pytest.mark.parametrize("tform", ["auto", "sparse"])
 @pytest.mark.parametrize("fused", ["1", "0"])
-def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
+def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused, tform):
     """Two processes, two GPUs, nothing but the C ABI between them (NCCL dlopen()ed by the library, unique id through
     a file, T tiles stored into the peer from the GEMM epilogue or all-gathered by NCCL): the row slabs must equal
     the single-GPU result bit for bit (same kernels, same order of additions) and the oracle within 1e-12."""
@@ -749,6 +802,8 @@ def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     nq, ns, nf, nt = 301, 150, 130, 91  # ragged: the last rank owns fewer rows / target columns
     os.environ["SS_FUSED_ALLGATHER"] = fused
+    if tform == "sparse":  # the edge-list form of the first product (csrc/ss_tsparse.cu), T tiles stored into the peer
+        os.environ["SS_T_FORM"] = "sparse"
     try:
         mpc = mp.get_context("spawn")
         path = str(tmp_path / "nccl_id")
@@ -760,6 +815,7 @@ def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
             assert p_.exitcode == 0
     finally:
         os.environ.pop("SS_FUSED_ALLGATHER", None)
+        os.environ.pop("SS_T_FORM", None)
     got = np.concatenate([np.load(tmp_path / f"r{r}.npy") for r in range(2)])
     flags = [open(tmp_path / f"r{r}.txt").read().split() for r in range(2)]
     assert all(f[0] == fused for f in flags) or fused == "1"  # fused falls back to NCCL without peer access
@@ -768,7 +824,12 @@ def test_sharded_c_abi_two_gpus(ss, o, tmp_path, fused):
     from simspread_b200._lib import SS_PREDICT_CLEAN, check
     ctx = ss.Context.default()
     dq, dx, dy, R = (ss.DMat.from_host(ctx, a) for a in (Xq, Xs, Y, np.zeros((nq, nt))))
-    check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+    if tform == "sparse":
+        os.environ["SS_T_FORM"] = "sparse"
+    try:
+        check(ss.lib().ss_predict_query(ctx.h, dq.h, dx.h, dy.h, R.h, SS_PREDICT_CLEAN, None))
+    finally:
+        os.environ.pop("SS_T_FORM", None)
     assert np.array_equal(got, R.to_host())
     want = o.predict_blocks_query(Xq, Xs, Y)
     o.clean_blocks(want, o.degrees_blocks(Xs, Y)[2])
