@@ -482,6 +482,15 @@ def run_b200(args):
         args.no_e2e = True
     r_times = [ms for ms, fl in prof if abs(fl - r_flops) < 0.5]
     t_times = [ms for ms, fl in prof if abs(fl - r_flops) >= 0.5]
+    # which form the first product took: the dense DMMA GEMM records 2 Ns Nf Nt flop, the edge-list form of a sparse label
+    # matrix (csrc/ss_tsparse.cu) 2 nnz(Y) Nf -- every entry of T is computed either way
+    t_fl = [fl for ms, fl in prof if abs(fl - r_flops) >= 0.5]
+    dense_t_flops = 2.0 * ns * nf * (nt // world if world > 1 else nt)
+    t_form = None
+    if t_fl:
+        t_form = ("dense DMMA GEMM (ss_dgemm_whole_kernel<!A_MMAJOR>)" if t_fl[0] > 0.5 * dense_t_flops else
+                  "edge list of the label matrix, %.1f %% dense (tsp_kernel: CSC of W by target column, FP64 FMA; "
+                  "SS_T_FORM=dense forces the DMMA GEMM)" % (100.0 * t_fl[0] / dense_t_flops))
     peak_meas = fp64_gemm_peak(torch, dev)
     roofline = None
     if r_times:
@@ -503,6 +512,7 @@ def run_b200(args):
             "flops_per_launch": r_flops, "ms_per_launch": statistics.mean(r_times),
             "share_of_step": statistics.mean(r_times) / ms_step,
             "t_gemm_ms": statistics.mean(t_times) if t_times else None,
+            "t_product": t_form,
         }
 
     # ---- parity spot check at full size (untimed): sampled entries recomputed with torch/cuBLAS -----

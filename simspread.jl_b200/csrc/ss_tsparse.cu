@@ -36,7 +36,7 @@ constexpr int TS_TPW = TS_TB / TS_WARPS;  // targets per warp
 constexpr int TS_THREADS = TS_WARPS * 32;
 constexpr int TS_SLAB_DOUBLES = TS_SB * TS_FB;
 constexpr size_t TS_SMEM = size_t(2) * TS_SLAB_DOUBLES * 8;  // 128 KB
-constexpr const char* kDefaultForm = "dense";
+constexpr const char* kDefaultForm = "auto";
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
