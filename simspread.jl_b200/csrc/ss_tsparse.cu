@@ -272,7 +272,7 @@ int32_t t_from_sparse_labels(ss_ctx* ctx, const double* Xs, int64_t ldxs, const 
     const bool force = !strcmp(form, "sparse");
     if (!force && strcmp(form, "auto")) return SS_OK;
     if (ns <= 0 || nf <= 0 || nt <= 0 || nmirror < 0 || nmirror > 7) return SS_OK;
-    if (ns >= (1ll << 31) || nf >= (1ll << 31) || nt >= (1ll << 31) || ceil_div(nf, TS_FB) > 65535) return SS_OK;
+    if (ns >= (1ll << 31) || nf >= (1ll << 31) || nt >= (1ll << 31) || ceil_div(nf, 32) > 65535) return SS_OK;  // grid.y limits
     // the dense DMMA product of a small problem is a few milliseconds: not worth a CSC build and a host round trip
     if (!force && 2.0 * double(ns) * double(nf) * double(nt) < 2e11) return SS_OK;
     if ((ldt & 1) || (reinterpret_cast<uintptr_t>(T) & 15)) return SS_OK;
@@ -290,7 +290,6 @@ int32_t t_from_sparse_labels(ss_ctx* ctx, const double* Xs, int64_t ldxs, const 
     SS_CHECK_CUDA(cudaMemsetAsync(nonfinite, 0, 4, ctx->stream));
     ts_scan_kernel<<<1, 1024, 0, ctx->stream>>>(kt, nt, col_ptr, total);
     {
-        SS_REQUIRE(ceil_div(nf, 32) <= 65535, "t_from_sparse_labels: too many features");
         const dim3 grid(unsigned(ceil_div(ns, 32)), unsigned(ceil_div(nf, 32)));
         transpose_check_kernel<<<grid, 256, 0, ctx->stream>>>(Xs, ldxs, XsT, ldf, ns, nf, nonfinite);
     }
