@@ -4,6 +4,7 @@
 #   bench    the bench line (N = 1), its ncu launch list            -> gpurun_out/bench_n1.json, launches_bench.csv
 #   kernels  per-kernel numbers of the HBM-bound passes             -> gpurun_out/kernels.json
 #   c5       sparse recommender: 5 % and 100 % of the users, ncu    -> gpurun_out/c5_*.json, c5_prof.ncu-rep
+#   tform    first product: dense DMMA GEMM vs the edge-list form of a sparse label matrix -> gpurun_out/tform.json
 #   prof     ncu --set full of the kernels changed late in round 2 (GEMM row bands on the C3 shape, CSR count / fill, top-L)
 #   n2 / n8  multi-GPU: C-ABI sharded test (n2), bench line, C5 sharded by users, reference arm under torchrun (n8)
 set -u
@@ -36,11 +37,13 @@ n8)
       tools/bench_multi.py --skip-c3 --skip-auc > gpurun_out/multi_n8.log 2>&1; tail -2 gpurun_out/multi_n8.log | cut -c1-600
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 \
       bench.py --impl reference --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_ref_n8.json 2> gpurun_out/bench_ref_n8.err; tail -c 400 gpurun_out/bench_ref_n8.json ;;
+tform)
+  timeout 300 python tools/bench_tform.py 2>&1 | tail -1 | cut -c1-900 ;;
 prof)
   python tools/profile_kernels_r02.py > gpurun_out/plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'ss_dgemm_kernel|csr_count|csr_fill|topl_warp' -s 4 -c 4 -o gpurun_out/r02_late_kernels \
       python tools/profile_kernels_r02.py > gpurun_out/ncu_late.log 2>&1
   ncu -i gpurun_out/r02_late_kernels.ncu-rep --page details --csv > gpurun_out/r02_ncu_late_kernels_setfull_details.csv 2>/dev/null
   tail -2 gpurun_out/ncu_late.log ;;
-*) echo "usage: tools/gpu_run.sh tests|bench|kernels|c5|n2|n8|prof"; exit 2 ;;
+*) echo "usage: tools/gpu_run.sh tests|bench|kernels|c5|n2|n8|prof|tform"; exit 2 ;;
 esac
