@@ -223,7 +223,10 @@ SS_API int32_t ss_ipc_close(ss_ctx* ctx, void* devptr);
 /* predict((A,B), ytest) for query rows [src/core.jl:402-423 with the blocks of :165-198]:
  *   R = Xq * T,  T = (Xs' ./ kf) * (Y ./ ks)      
  * Xq: Nq x Nf, Xs: Ns x Nf, Y: Ns x Nt, R: Nq x Nt.  Runs degrees -> spread -> T -> R on the
- * context stream.  kt_out (optional) receives the target degrees used by clean!. */
+ * context stream.  kt_out (optional) receives the target degrees used by clean!.
+ * T is a dense FP64 tensor-core product, or -- for large problems whose label matrix Y is at most 10 % dense and whose
+ * feature weights are finite -- a sum over the edges of Y in ascending source order (same value to ~1e-15, independent
+ * of tiles and shards; environment SS_T_FORM=dense|sparse|auto overrides the choice). */
 SS_API int32_t ss_predict_query(ss_ctx* ctx, const ss_mat* Xq, const ss_mat* Xs, const ss_mat* Y, ss_mat* R,
                          uint32_t flags, ss_ivec* kt_out);
 /* The same chain with the result delivered to host memory [the `F[names(ytest,1), names(ytest,2)]` that
